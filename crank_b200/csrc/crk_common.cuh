@@ -1,0 +1,125 @@
+// crank-b200: shared device helpers for the fp32 (CUDA-core) kernel family.
+//
+// Data layout everywhere: channels-last.  An activation is a row-major (B*T, C) panel,
+// "(batch*time) x channel", row stride `ld` floats (so sub-ranges of a concatenated buffer can be
+// addressed without a copy).  A CTA owns a tile of TM=64 consecutive frames of ONE utterance,
+// so "same"/causal zero padding never bleeds across utterances.
+//
+// Thread mapping of every tile GEMM (256 threads): ty = tid/32 owns 8 consecutive tile rows,
+// tx = tid%32 owns CPT consecutive output columns (TN = 32*CPT <= 128).  All lanes of a warp
+// share ty, so A-operand shared-memory reads are broadcasts; B-operand reads are CPT*4-byte
+// vectors, conflict free.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CRK_THREADS 256
+#define CRK_TM 64
+
+#define CRK_ACT_NONE 0
+#define CRK_ACT_RELU 1
+#define CRK_ACT_LRELU 2
+
+#define CRK_SQRT_HALF 0.70710678118654752440f
+
+// error codes of the C ABI (see include/crank_b200.h)
+#define CRK_OK 0
+#define CRK_ERR_ARG (-1)
+#define CRK_ERR_CUDA (-2)
+#define CRK_ERR_UNSUPPORTED (-3)
+
+namespace crk {
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline long long cdivl(long long a, long long b) { return (a + b - 1) / b; }
+
+// columns-per-thread needed for n output columns (TN = 32*cpt)
+__host__ __device__ inline int cpt_for(int n) { return n <= 32 ? 1 : n <= 64 ? 2 : n <= 96 ? 3 : 4; }
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == CRK_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == CRK_ACT_LRELU) return v > 0.f ? v : v * slope;
+    return v;
+}
+// derivative of the activation, evaluated from the activation's OUTPUT (sign-preserving acts)
+__device__ __forceinline__ float act_grad(float out, int act, float slope) {
+    if (act == CRK_ACT_RELU) return out > 0.f ? 1.f : 0.f;
+    if (act == CRK_ACT_LRELU) return out > 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+template <int CPT>
+__device__ __forceinline__ void load_b(float (&b)[CPT], const float* p) {
+    if constexpr (CPT == 4) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+    } else if constexpr (CPT == 2) {
+        float2 v = *reinterpret_cast<const float2*>(p);
+        b[0] = v.x; b[1] = v.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) b[c] = p[c];
+    }
+}
+
+// acc[i][c] += sum_kk A[i][kk] * B[kk][c];  A row-major in smem (row stride lda, lda%4==0,
+// 16B-aligned), K%4==0.  `A` already points at this thread's first row, `Bm` at its first column.
+template <int CPT>
+__device__ __forceinline__ void tile_mac_rowA(float (&acc)[8][CPT], const float* __restrict__ A,
+                                              int lda, const float* __restrict__ Bm, int ldb, int K) {
+    for (int kk = 0; kk < K; kk += 4) {
+        float4 a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(A + i * lda + kk);
+        float b[CPT];
+        load_b<CPT>(b, Bm + (kk + 0) * ldb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(a[i].x, b[c], acc[i][c]);
+        load_b<CPT>(b, Bm + (kk + 1) * ldb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(a[i].y, b[c], acc[i][c]);
+        load_b<CPT>(b, Bm + (kk + 2) * ldb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(a[i].z, b[c], acc[i][c]);
+        load_b<CPT>(b, Bm + (kk + 3) * ldb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(a[i].w, b[c], acc[i][c]);
+    }
+}
+
+// acc[i][c] += sum_kk A[kk][i] * B[kk][c];  A "column-major": smem [K][lda], the thread's 8 rows
+// are 8 consecutive floats (16B aligned).  Used by wgrad (reduction index = frame).
+template <int CPT>
+__device__ __forceinline__ void tile_mac_colA(float (&acc)[8][CPT], const float* __restrict__ A,
+                                              int lda, const float* __restrict__ Bm, int ldb, int K) {
+#pragma unroll 4
+    for (int kk = 0; kk < K; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(A + kk * lda);
+        const float4 a1 = *reinterpret_cast<const float4*>(A + kk * lda + 4);
+        float b[CPT];
+        load_b<CPT>(b, Bm + kk * ldb);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(a[i], b[c], acc[i][c]);
+    }
+}
+
+// cooperative copy of n floats (n%4==0, both 16B aligned) global->shared
+__device__ __forceinline__ void copy_to_smem(float* dst, const float* __restrict__ src, int n) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = threadIdx.x; i < n / 4; i += CRK_THREADS) d4[i] = __ldg(s4 + i);
+}
+
+}  // namespace crk

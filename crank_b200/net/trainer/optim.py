@@ -1,0 +1,35 @@
+"""Fused Adam over flat parameter packs (crk_adam_step): torch.optim.Adam semantics
+(crank/net/trainer/utils.py:43 -> Adam(lr) with default betas/eps, no weight decay / amsgrad).
+Each network owns a handful of flat parameters (see parallel_wavegan.models), so a step is a
+handful of launches instead of the reference's per-tensor loop over 200+ tiny tensors."""
+
+import torch
+
+from ... import ops
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                ops.adam_step(p.data, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), b1, b2,
+                              group["eps"], st["step"])
+        return loss

@@ -1,0 +1,325 @@
+"""torch.autograd bindings of the C-ABI kernels (argument checking + pointer extraction only).
+
+Activations are channels-last (B, T, C) fp32 CUDA tensors; the reference's (B, C, T) layout only
+exists at the public module boundaries (crank_b200.parallel_wavegan.models).
+"""
+
+import ctypes as C
+import math
+
+import torch
+
+from . import lib as L
+
+_f32 = torch.float32
+
+
+def panel(t):
+    """(tensor, ld) for a (B,T,C) fp32 tensor viewed as a (B*T, C) row panel with row stride ld."""
+    if t is None:
+        return None, 0
+    if t.dtype != _f32:
+        t = t.float()
+    L.require_cuda(t)
+    assert t.dim() == 3, "expected (B, T, C)"
+    B, T, Cn = t.shape
+    if t.stride(2) != 1 or (B > 1 and t.stride(0) != T * t.stride(1)) or t.stride(1) < Cn or (
+        t.data_ptr() % 4
+    ):
+        t = t.contiguous()
+    return t, t.stride(1)
+
+
+def _empty(n, device):
+    return torch.empty(max(int(n), 4), dtype=_f32, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+class WavenetFn(torch.autograd.Function):
+    """One WaveNet stack (first 1x1, L gated residual blocks, head) -- crk_wavenet_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, net, x, c, dropmul, theta):
+        x, ldx = panel(x)
+        c, ldc = panel(c)
+        B, T, _ = x.shape
+        cfg = net.cfg
+        weff = net.effective_weights()
+        y = torch.empty(B, T, cfg.out_ch, dtype=_f32, device=x.device)
+        act = _empty(L.lib().crk_wavenet_act_floats(C.byref(cfg), B, T), x.device)
+        L.call("crk_wavenet_fwd", C.byref(cfg), L.ptr(weff), L.ptr(x), ldx, L.ptr(c), ldc,
+               L.ptr(dropmul), L.ptr(y), cfg.out_ch, L.ptr(act), B, T)
+        ctx.net = net
+        ctx.dims = (B, T, ldx, ldc)
+        ctx.has_c = c is not None
+        ctx.has_drop = dropmul is not None
+        saved = [x, theta, weff, act]
+        if c is not None:
+            saved.append(c)
+        if dropmul is not None:
+            saved.append(dropmul)
+        ctx.save_for_backward(*saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved = list(ctx.saved_tensors)
+        x, theta, weff, act = saved[:4]
+        rest = saved[4:]
+        c = rest.pop(0) if ctx.has_c else None
+        dropmul = rest.pop(0) if ctx.has_drop else None
+        B, T, ldx, ldc = ctx.dims
+        cfg = ctx.net.cfg
+        dy, lddy = panel(dy)
+        need_dx = ctx.needs_input_grad[1]
+        need_dc = ctx.has_c and ctx.needs_input_grad[2]
+        dx = torch.empty(B, T, cfg.in_ch, dtype=_f32, device=x.device) if need_dx else None
+        dc = torch.empty(B, T, cfg.aux_ch, dtype=_f32, device=x.device) if need_dc else None
+        gtheta = torch.empty_like(theta)
+        ws = _empty(L.lib().crk_wavenet_ws_floats(C.byref(cfg), B, T), x.device)
+        L.call("crk_wavenet_bwd", C.byref(cfg), L.ptr(theta), L.ptr(weff), L.ptr(x), ldx,
+               L.ptr(c), ldc, L.ptr(dropmul), L.ptr(act), L.ptr(dy), lddy,
+               L.ptr(dx), cfg.in_ch, L.ptr(dc), max(cfg.aux_ch, 0), L.ptr(gtheta), L.ptr(ws), B, T)
+        return None, dx, dc, None, gtheta
+
+
+class ConvstackFn(torch.autograd.Function):
+    """Plain Conv1d+LeakyReLU stack -- crk_convstack_fwd / _bwd.  dx_scale folds a gradient
+    reversal layer (crank/net/module/spkradv.py:63-72) into the input gradient."""
+
+    @staticmethod
+    def forward(ctx, net, x, theta, dx_scale):
+        x, ldx = panel(x)
+        B, T, _ = x.shape
+        cfg = net.cfg
+        weff = net.effective_weights()
+        y = torch.empty(B, T, cfg.out_ch, dtype=_f32, device=x.device)
+        act = _empty(L.lib().crk_convstack_act_floats(C.byref(cfg), B, T), x.device)
+        L.call("crk_convstack_fwd", C.byref(cfg), L.ptr(weff), L.ptr(x), ldx, L.ptr(y), cfg.out_ch,
+               L.ptr(act), B, T)
+        ctx.net = net
+        ctx.dims = (B, T, ldx)
+        ctx.dx_scale = float(dx_scale)
+        ctx.save_for_backward(x, theta, weff, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, theta, weff, act = ctx.saved_tensors
+        B, T, ldx = ctx.dims
+        cfg = ctx.net.cfg
+        dy, lddy = panel(dy)
+        need_dx = ctx.needs_input_grad[1]
+        dx = torch.empty(B, T, cfg.in_ch, dtype=_f32, device=x.device) if need_dx else None
+        gtheta = torch.empty_like(theta)
+        ws = _empty(L.lib().crk_convstack_ws_floats(C.byref(cfg), B, T), x.device)
+        L.call("crk_convstack_bwd", C.byref(cfg), L.ptr(theta), L.ptr(weff), L.ptr(x), ldx,
+               L.ptr(act), L.ptr(dy), lddy, L.ptr(dx), cfg.in_ch, C.c_float(ctx.dx_scale),
+               L.ptr(gtheta), L.ptr(ws), B, T)
+        return None, dx, gtheta, None
+
+
+# ---------------------------------------------------------------------------------------------
+class VQFn(torch.autograd.Function):
+    """idx = argmin L2, e = W[idx], qx = x + (e - x) (straight-through).  crk_vq_argmin."""
+
+    @staticmethod
+    def forward(ctx, x, W):
+        x, ldx = panel(x)
+        B, T, D = x.shape
+        K = W.shape[0]
+        dev = x.device
+        Wc = W.detach()
+        if not Wc.is_contiguous():
+            Wc = Wc.contiguous()
+        WT = torch.empty(D, K, dtype=_f32, device=dev)
+        wn = torch.empty(K, dtype=_f32, device=dev)
+        L.call("crk_vq_prepare", L.ptr(Wc), L.ptr(WT), L.ptr(wn), K, D)
+        idx = torch.empty(B, T, dtype=torch.int64, device=dev)
+        e = torch.empty(B, T, D, dtype=_f32, device=dev)
+        qx = torch.empty(B, T, D, dtype=_f32, device=dev)
+        L.call("crk_vq_argmin", L.ptr(x), ldx, L.ptr(Wc), L.ptr(WT), L.ptr(wn), L.ptr(idx),
+               L.ptr(e), D, L.ptr(qx), D, B * T, K, D)
+        ctx.save_for_backward(idx)
+        ctx.KD = (K, D)
+        ctx.mark_non_differentiable(idx)
+        return e, qx, idx
+
+    @staticmethod
+    def backward(ctx, ge, gqx, _gidx):
+        (idx,) = ctx.saved_tensors
+        K, D = ctx.KD
+        gx = gqx if ctx.needs_input_grad[0] else None
+        gW = None
+        if ctx.needs_input_grad[1] and ge is not None:
+            ge, ldg = panel(ge)
+            gW = torch.zeros(K, D, dtype=_f32, device=ge.device)
+            L.call("crk_vq_scatter_grad", L.ptr(ge), ldg, L.ptr(idx), L.ptr(gW), idx.numel(), K, D)
+        return gx, gW
+
+
+def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None):
+    """EMA codebook update (vqvae2.py:315-330).  `reduce_fn(flat_stats)` sums [counts | esum]
+    across data-parallel ranks before the normalisation."""
+    x, ldx = panel(x)
+    B, T, D = x.shape
+    K = W.shape[0]
+    dev = x.device
+    stats = torch.empty(K + D * K, dtype=_f32, device=dev)
+    ws = _empty(L.lib().crk_vq_stats_ws_floats(B * T, K, D), dev)
+    counts = stats[:K]
+    esum = stats[K:]
+    L.call("crk_vq_stats", L.ptr(x), ldx, L.ptr(idx), L.ptr(counts), L.ptr(esum), L.ptr(ws),
+           B * T, K, D)
+    if reduce_fn is not None:
+        reduce_fn(stats)
+    L.call("crk_vq_ema", L.ptr(counts), L.ptr(esum), L.ptr(ema_size), L.ptr(ema_w), L.ptr(W),
+           C.c_float(decay), C.c_float(eps), K, D)
+
+
+# ---------------------------------------------------------------------------------------------
+def _mask_u8(mask, B, T):
+    if mask is None:
+        return None
+    m = mask.reshape(B, T)
+    if m.dtype == torch.bool:
+        m = m.contiguous().view(torch.uint8)
+    elif m.dtype != torch.uint8:
+        m = (m != 0).view(torch.uint8)
+    return m.contiguous()
+
+
+class MaskedLossFn(torch.autograd.Function):
+    """(mean |x-y|, mean (x-y)^2) over mask-selected frames with causal shift.  y may be a python
+    float (LSGAN targets).  Returns two 0-dim tensors; no host sync."""
+
+    @staticmethod
+    def forward(ctx, x, y, mask, shift):
+        x, ldx = panel(x)
+        B, T, D = x.shape
+        yconst = 0.0
+        yt, ldy = None, 0
+        if isinstance(y, torch.Tensor):
+            yt, ldy = panel(y.detach())
+        else:
+            yconst = float(y)
+        m = _mask_u8(mask, B, T)
+        out = torch.empty(3, dtype=_f32, device=x.device)
+        ws = _empty(L.lib().crk_masked_loss_ws_floats(B, T, D), x.device)
+        L.call("crk_masked_loss_fwd", L.ptr(x), ldx, L.ptr(yt), ldy, C.c_float(yconst), L.ptr(m),
+               B, T, D, int(shift), L.ptr(out), L.ptr(ws))
+        ctx.meta = (B, T, D, ldx, ldy, yconst, int(shift))
+        ctx.has_y = yt is not None
+        ctx.has_m = m is not None
+        saved = [x, out]
+        if yt is not None:
+            saved.append(yt)
+        if m is not None:
+            saved.append(m)
+        ctx.save_for_backward(*saved)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        saved = list(ctx.saved_tensors)
+        x, out = saved[:2]
+        rest = saved[2:]
+        yt = rest.pop(0) if ctx.has_y else None
+        m = rest.pop(0) if ctx.has_m else None
+        B, T, D, ldx, ldy, yconst, shift = ctx.meta
+        if g1 is not None:
+            g1 = g1.contiguous()
+        if g2 is not None:
+            g2 = g2.contiguous()
+        dx = torch.empty(B, T, D, dtype=_f32, device=x.device)
+        L.call("crk_masked_loss_bwd", L.ptr(x), ldx, L.ptr(yt), ldy, C.c_float(yconst), L.ptr(m),
+               B, T, D, shift, L.ptr(out), L.ptr(g1), L.ptr(g2), L.ptr(dx), D)
+        return dx, None, None, None
+
+
+def masked_l1_mse(x, y, mask=None, shift=0):
+    return MaskedLossFn.apply(x, y, mask, shift)
+
+
+class StftLossFn(torch.autograd.Function):
+    """STFT-magnitude trajectory L1 for ONE (n_fft, hop, win) resolution; returns (mag, logmag) means."""
+
+    @staticmethod
+    def forward(ctx, x, y, n_fft, hop, win):
+        x, ldx = panel(x)
+        y, ldy = panel(y.detach())
+        B, T, D = x.shape
+        out = torch.empty(2, dtype=_f32, device=x.device)
+        ws = _empty(L.lib().crk_stft_loss_ws_floats(B, T, D, n_fft, hop), x.device)
+        L.call("crk_stft_loss_fwd", L.ptr(x), ldx, L.ptr(y), ldy, B, T, D, n_fft, hop, win,
+               L.ptr(out), L.ptr(ws))
+        ctx.meta = (B, T, D, ldx, ldy, n_fft, hop, win)
+        ctx.save_for_backward(x, y)
+        o0, o1 = out[0], out[1]
+        ctx.mark_non_differentiable(o1)
+        return o0, o1
+
+    @staticmethod
+    def backward(ctx, g, _glog):
+        x, y = ctx.saved_tensors
+        B, T, D, ldx, ldy, n_fft, hop, win = ctx.meta
+        dx = torch.empty(B, T, D, dtype=_f32, device=x.device)
+        L.call("crk_stft_loss_bwd", L.ptr(x), ldx, L.ptr(y), ldy, B, T, D, n_fft, hop, win,
+               L.ptr(g.contiguous()), C.c_float(1.0), L.ptr(dx), D, 0)
+        return dx, None, None, None, None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        L.require_cuda(logits, labels)
+        assert logits.dim() == 2
+        if logits.stride(1) != 1:
+            logits = logits.contiguous()
+        logits = logits.float()
+        labels = labels.contiguous()
+        Fn, S = logits.shape
+        out = torch.empty(2, dtype=_f32, device=logits.device)
+        ws = _empty(L.lib().crk_ce_ws_floats(Fn), logits.device)
+        L.call("crk_ce_fwd", L.ptr(logits), logits.stride(0), L.ptr(labels), Fn, S,
+               int(ignore_index), L.ptr(out), L.ptr(ws))
+        ctx.meta = (Fn, S, int(ignore_index))
+        ctx.save_for_backward(logits, labels, out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, out = ctx.saved_tensors
+        Fn, S, ign = ctx.meta
+        dl = torch.empty(Fn, S, dtype=_f32, device=logits.device)
+        L.call("crk_ce_bwd", L.ptr(logits), logits.stride(0), L.ptr(labels), Fn, S, ign,
+               L.ptr(out), L.ptr(g.contiguous()), L.ptr(dl), S)
+        return dl, None, None
+
+
+def cross_entropy(logits, labels, ignore_index=-100):
+    return CrossEntropyFn.apply(logits, labels, ignore_index)
+
+
+# ---------------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step_count):
+    L.require_cuda(p, g, m, v)
+    L.call("crk_adam_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), C.c_float(lr),
+           C.c_float(beta1), C.c_float(beta2), C.c_float(eps), int(step_count))
+
+
+def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None):
+    """wav (B, n_samples) -> (B, n_frames, n_mels);  frames start at m*hop (no centring here)."""
+    L.require_cuda(wav, window, mel_basis)
+    wav = wav.float().contiguous()
+    B, n = wav.shape
+    n_mels = mel_basis.shape[1]
+    M = 1 + (n - n_fft) // hop
+    out = torch.empty(B, M, n_mels, dtype=_f32, device=wav.device)
+    ws = _empty(L.lib().crk_logmel_ws_floats(B, M, n_fft), wav.device)
+    L.call("crk_logmel_fwd", L.ptr(wav), B, n, L.ptr(window), L.ptr(mel_basis), n_fft, hop,
+           n_mels, C.c_float(eps), L.ptr(mean), L.ptr(std), L.ptr(out), L.ptr(ws))
+    return out
+
+
+SQRT_HALF = math.sqrt(0.5)

@@ -1,0 +1,194 @@
+/* crank_b200 -- C ABI of libcrank_b200.so (sm_100a CUDA kernels for crank's VQ-VAE train step).
+ *
+ * The reference (k2kobayashi/crank) is pure Python on PyTorch: it has no FFI layer.  Its seam is
+ * the L2/L1 boundary of SURVEY.md section 8b -- Python classes whose arithmetic is stock torch ops.  This
+ * header is what a maintainer binds (ctypes) to replace that arithmetic; each
+ * entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 (CRK_OK) or a negative error code; crk_strerror() names it.
+ *     No exceptions cross the ABI.
+ *   - all tensor arguments are DEVICE pointers owned by the caller (PyTorch allocations); the
+ *     library never allocates persistent memory -- scratch sizes come from the *_floats() queries.
+ *   - activations are channels-last fp32 panels (B*T, C) with an explicit row stride ("ld", floats).
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it, capturable in CUDA
+ *     graphs (no host syncs, no mallocs), re-entrant per stream.
+ *   - single training thread per process, one process per GPU.
+ */
+#ifndef CRANK_B200_H
+#define CRANK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRK_OK 0
+#define CRK_ERR_ARG (-1)
+#define CRK_ERR_CUDA (-2)
+#define CRK_ERR_UNSUPPORTED (-3)
+
+const char* crk_strerror(int code);
+/* last CUDA error string seen by the library on this thread (for CRK_ERR_CUDA) */
+const char* crk_last_cuda_error(void);
+int crk_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * WaveNet stack = parallel_wavegan.models.ParallelWaveGANGenerator (upsample off) and
+ * ResidualParallelWaveGANDiscriminator.   Replaces: crank/net/module/vqvae2.py:236-273 (encoders /
+ * decoders), crank/bin/train.py:107-115 (residual discriminator D).
+ * 64 residual / 128 gate / 64 skip channels are fixed (the reference never changes them).
+ */
+typedef struct {
+    int in_ch, out_ch, aux_ch;   /* aux_ch <= 0: no conditioning */
+    int layers, stacks;          /* dilation of layer l = 2^(l % (layers/stacks)) */
+    int kernel_size;
+    int causal;                  /* 0: "same" padding, 1: left padding (k-1)*d */
+    int first_act;               /* 0: none (generator), 2: LeakyReLU after first 1x1 (discriminator) */
+    int head_act;                /* 1: ReLU (generator), 2: LeakyReLU (discriminator) */
+    float slope;                 /* LeakyReLU negative slope */
+} crk_wavenet_cfg;
+
+/* One weight-normalised Conv1d inside a parameter pack ("theta": [g | v | bias] per conv,
+ * PyTorch weight_norm layout: weight_g (Cout,1,1), weight_v (Cout,Cin,k), bias (Cout)). */
+typedef struct {
+    int g_off, v_off, b_off;     /* offsets (floats) into theta; b_off < 0: no bias */
+    int cout, cin, k;
+    int w_off, bias_off;         /* offsets into the packed effective-weight buffer ("weff") */
+    int cin_pad, ldw, perm;      /* fwd packing  W[j][cin_pad][ldw], column permutation id */
+    int wt_off, wt_rows, ldwt;   /* transposed, tap-flipped copy for dgrad; wt_off < 0: none */
+} crk_conv_desc;
+
+#define CRK_MAX_CONVS 64
+
+/* number of convs, canonical order: first_conv, then per layer {conv, [conv1x1_aux], conv1x1_out,
+ * conv1x1_skip}, then last_conv_layers.1, last_conv_layers.3.  descs may be NULL. */
+int crk_wavenet_describe(const crk_wavenet_cfg* cfg, crk_conv_desc* descs, int* n_convs,
+                         long long* theta_floats, long long* weff_floats);
+long long crk_wavenet_act_floats(const crk_wavenet_cfg* cfg, int B, int T);
+long long crk_wavenet_ws_floats(const crk_wavenet_cfg* cfg, int B, int T);
+
+/* weight-norm forward: theta -> weff  (w = g * v/||v||, packed + transposed copies).
+ * Replaces torch._weight_norm evaluated at every conv call (511x per LSGAN step in the reference). */
+int crk_wavenet_weights(const crk_wavenet_cfg* cfg, const float* theta, float* weff, void* stream);
+
+/* forward.  x (B*T,in_ch) ld ldx; c (B*T,aux_ch) ld ldc or NULL; dropmul [layers][B*T][64]
+ * dropout multipliers (mask/(1-p)) or NULL; y (B*T,out_ch) ld ldy; act: saved activations
+ * (crk_wavenet_act_floats), needed by backward. */
+int crk_wavenet_fwd(const crk_wavenet_cfg* cfg, const float* weff, const float* x, int ldx,
+                    const float* c, int ldc, const float* dropmul, float* y, int ldy, float* act,
+                    int B, int T, void* stream);
+
+/* backward.  dy (B*T,out_ch) ld lddy -> gtheta (same layout as theta, overwritten),
+ * dx (B*T,in_ch) ld lddx or NULL, dc (B*T,aux_ch) ld lddc or NULL (overwritten).
+ * ws: scratch of crk_wavenet_ws_floats() floats. */
+int crk_wavenet_bwd(const crk_wavenet_cfg* cfg, const float* theta, const float* weff,
+                    const float* x, int ldx, const float* c, int ldc, const float* dropmul,
+                    const float* act, const float* dy, int lddy, float* dx, int lddx, float* dc,
+                    int lddc, float* gtheta, float* ws, int B, int T, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Plain conv stack = parallel_wavegan.models.ParallelWaveGANDiscriminator (Conv1d + LeakyReLU).
+ * Replaces: crank/bin/train.py:78-89 (speaker classifier C), crank/net/module/spkradv.py:49-60.
+ */
+typedef struct {
+    int in_ch, out_ch, layers, kernel_size, conv_ch, dilation_factor;
+    float slope;
+} crk_convstack_cfg;
+
+int crk_convstack_describe(const crk_convstack_cfg* cfg, crk_conv_desc* descs, int* n_convs,
+                           long long* theta_floats, long long* weff_floats);
+long long crk_convstack_act_floats(const crk_convstack_cfg* cfg, int B, int T);
+long long crk_convstack_ws_floats(const crk_convstack_cfg* cfg, int B, int T);
+int crk_convstack_weights(const crk_convstack_cfg* cfg, const float* theta, float* weff, void* stream);
+int crk_convstack_fwd(const crk_convstack_cfg* cfg, const float* weff, const float* x, int ldx,
+                      float* y, int ldy, float* act, int B, int T, void* stream);
+/* dx_scale multiplies dx (gradient-reversal layer of crank/net/module/spkradv.py:63-72: -lambda) */
+int crk_convstack_bwd(const crk_convstack_cfg* cfg, const float* theta, const float* weff,
+                      const float* x, int ldx, const float* act, const float* dy, int lddy,
+                      float* dx, int lddx, float dx_scale, float* gtheta, float* ws, int B, int T,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Vector quantiser.  Replaces Quantizer.vq / Quantizer.forward, crank/net/module/vqvae2.py:306-347.
+ *   crk_vq_prepare : codebook W (K,D) -> WT (D,K) and wn[k] = sum_d W[k][d]^2
+ *   crk_vq_argmin  : idx[f] = argmin_k fl(fl(wn[k] - 2*dot(x_f, w_k)) + |x_f|^2)   (lowest index wins ties)
+ *                    e[f] = W[idx[f]],  qx[f] = x[f] + (e[f] - x[f])   (straight-through value)
+ *   crk_vq_stats   : counts[k] = #{f: idx[f]=k},  esum[d][k] = sum_{f: idx[f]=k} x[f][d]   (deterministic)
+ *   crk_vq_ema     : EMA update + Laplace smoothing + new codebook (vqvae2.py:315-330)
+ * D must be 64, K a multiple of 128 (the reference uses D=64, K=512).
+ */
+int crk_vq_prepare(const float* W, float* WT, float* wn, int K, int D, void* stream);
+int crk_vq_argmin(const float* x, int ldx, const float* W, const float* WT, const float* wn,
+                  long long* idx, float* e, int lde, float* qx, int ldqx, long long F, int K, int D,
+                  void* stream);
+long long crk_vq_stats_ws_floats(long long F, int K, int D);
+int crk_vq_stats(const float* x, int ldx, const long long* idx, float* counts, float* esum,
+                 float* ws, long long F, int K, int D, void* stream);
+int crk_vq_ema(const float* counts, const float* esum, float* ema_size, float* ema_w, float* W,
+               float decay, float eps, int K, int D, void* stream);
+/* dW[k][d] += sum_{f: idx[f]=k} g[f][d]  (gradient of the codebook gather; only without EMA) */
+int crk_vq_scatter_grad(const float* g, int ldg, const long long* idx, float* dW, long long F,
+                        int K, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Losses.  Each *_fwd writes a small fp32 record to `out` (device) and *_bwd reads the upstream
+ * scalar gradient(s) from device memory -- no host synchronisation (the reference syncs via
+ * masked_select and .item(), crank/net/trainer/trainer_vqvae.py:229-237, basetrainer.py:208-215).
+ */
+/* masked L1 / MSE with causal shift (crank/net/module/loss.py:30-47, trainer_vqvae.py:214-232,
+ * trainer_lsgan.py:154-171).  x,y (B,T,D); y NULL => compare against the constant yconst;
+ * mask (B,T) uint8 or NULL.  shift s>=0: x[:, s:] vs y[:, :T-s] with mask[:, s:];
+ * s<0: x[:, :T+s] vs y[:, -s:] with mask[:, :T+s].  out[0]=mean|d|, out[1]=mean d^2, out[2]=#elements. */
+int crk_masked_loss_fwd(const float* x, int ldx, const float* y, int ldy, float yconst,
+                        const unsigned char* mask, int B, int T, int D, int shift, float* out,
+                        float* ws, void* stream);
+long long crk_masked_loss_ws_floats(int B, int T, int D);
+/* dx = g_l1[0]*sign(d)/n + g_mse[0]*2d/n on selected elements, 0 elsewhere (g_* may be NULL) */
+int crk_masked_loss_bwd(const float* x, int ldx, const float* y, int ldy, float yconst,
+                        const unsigned char* mask, int B, int T, int D, int shift,
+                        const float* out, const float* g_l1, const float* g_mse, float* dx, int lddx,
+                        void* stream);
+
+/* STFT-magnitude trajectory L1 (crank/net/module/loss.py:50-85): each feature dimension's time
+ * trajectory -> STFT(n_fft, hop, hann(win) centred in n_fft, center=True reflect) ->
+ * sqrt(clamp(re^2+im^2, 1e-7)) -> mean |mag_x - mag_y|.   out[0] = loss. */
+long long crk_stft_loss_ws_floats(int B, int T, int D, int n_fft, int hop);
+int crk_stft_loss_fwd(const float* x, int ldx, const float* y, int ldy, int B, int T, int D,
+                      int n_fft, int hop, int win, float* out, float* ws, void* stream);
+/* dx (+)= g[0] * scale * dLoss/dx   (accumulate != 0 adds into dx) */
+int crk_stft_loss_bwd(const float* x, int ldx, const float* y, int ldy, int B, int T, int D,
+                      int n_fft, int hop, int win, const float* g, float scale, float* dx, int lddx,
+                      int accumulate, void* stream);
+
+/* cross entropy with ignore_index (torch.nn.CrossEntropyLoss(ignore_index=-100),
+ * crank/net/trainer/utils.py:26).  logits (F,S) ld ldl, S<=64; out[0]=loss, out[1]=#valid rows */
+long long crk_ce_ws_floats(long long F);
+int crk_ce_fwd(const float* logits, int ldl, const long long* labels, long long F, int S,
+               long long ignore_index, float* out, float* ws, void* stream);
+int crk_ce_bwd(const float* logits, int ldl, const long long* labels, long long F, int S,
+               long long ignore_index, const float* out, const float* g, float* dlogits, int lddl,
+               void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Adam (torch.optim.Adam defaults, crank/net/trainer/utils.py:43; step_model trainer_vqvae.py:200-208).
+ * state: m, v same size as p; step_count is the 1-based step number AFTER this update. */
+int crk_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                  float beta2, float eps, int step_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Log-mel front end (crank/net/module/mlfb.py:134-171 online; crank/feature/feature.py:126-145 offline):
+ * frames of n_fft samples every `hop`, times window, |rFFT|, x mel basis (n_bins x n_mels), clamp eps,
+ * log10, optional (x-mean)/std.   wav (B, n_samples) already padded by the caller (center handling is
+ * host-side index arithmetic); n_frames = 1 + (n_samples - n_fft)/hop. */
+long long crk_logmel_ws_floats(int B, int n_frames, int n_fft);
+int crk_logmel_fwd(const float* wav, int B, long long n_samples, const float* window,
+                   const float* mel_basis, int n_fft, int hop, int n_mels, float eps,
+                   const float* mean, const float* stdv, float* out, float* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRANK_B200_H */
