@@ -12,6 +12,7 @@
 #include "crk_loss.cuh"
 #include "crk_resblock.cuh"
 #include "crk_stacks.cuh"
+#include "crk_tc_probe.cuh"
 #include "crk_vq.cuh"
 
 namespace crk {
@@ -43,6 +44,52 @@ const char* crk_strerror(int code) {
 }
 const char* crk_last_cuda_error(void) { return g_cuda_err; }
 int crk_version(void) { return 100; }
+
+unsigned long long crk_launch_count(void) { return instr().launches; }
+int crk_timing_enable(int kernel_id) {
+    Instr& I = instr();
+    if (kernel_id < 0 || kernel_id >= CRK_K_MAX) return CRK_ERR_ARG;
+    if (kernel_id > 0 && !I.ev) {
+        I.ev = new cudaEvent_t[2 * Instr::kMaxPairs];
+        for (int i = 0; i < 2 * Instr::kMaxPairs; ++i) API_TRY(cudaEventCreate(&I.ev[i]));
+    }
+    I.enabled_id = kernel_id;
+    I.npairs = 0;
+    return CRK_OK;
+}
+int crk_timing_read(int* count, float* total_ms) {
+    Instr& I = instr();
+    if (!count || !total_ms) return CRK_ERR_ARG;
+    API_TRY(cudaDeviceSynchronize());
+    float tot = 0.f;
+    for (int i = 0; i < I.npairs; ++i) {
+        float ms = 0.f;
+        API_TRY(cudaEventElapsedTime(&ms, I.ev[2 * i], I.ev[2 * i + 1]));
+        tot += ms;
+    }
+    *count = I.npairs;
+    *total_ms = tot;
+    I.npairs = 0;
+    return CRK_OK;
+}
+
+// ---- tcgen05 probe ---------------------------------------------------------------------------
+int crk_tc_probe(const float* A, int lda, int rowsA, const float* B, int ldb, int rowsB, float* D, int N,
+                 int K, int row_shift, int mode, int split, void* stream) {
+    if (!A || !B || !D || (N != 64 && N != 128) || K < 8 || (K % 8) != 0 || row_shift < 0) return CRK_ERR_ARG;
+    if (mode == 0 && (rowsA < 128 + row_shift || rowsB < N)) return CRK_ERR_ARG;
+    if (mode == 1 && (rowsA < K || rowsB < K)) return CRK_ERR_ARG;
+    TcProbeParams p;
+    p.A = A; p.lda = lda; p.rowsA = rowsA; p.B = B; p.ldb = ldb; p.rowsB = rowsB; p.D = D;
+    p.N = N; p.K = K; p.row_shift = row_shift; p.mode = mode; p.split = split;
+    const int colsA = mode == 0 ? K : 128, colsB = mode == 0 ? K : N;
+    const size_t smem = (size_t)2 * ((colsA / 4) * tc::chunk_stride_bytes(rowsA) + (colsB / 4) * tc::chunk_stride_bytes(rowsB));
+    if (smem > 200 * 1024) return CRK_ERR_UNSUPPORTED;
+    API_TRY(cudaFuncSetAttribute(k_tc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_tc_probe<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
 
 // ---- WaveNet stack ---------------------------------------------------------------------------
 int crk_wavenet_describe(const crk_wavenet_cfg* cfg, crk_conv_desc* descs, int* n_convs,
@@ -132,7 +179,7 @@ int crk_convstack_bwd(const crk_convstack_cfg* cfg, const float* theta, const fl
 int crk_vq_prepare(const float* W, float* WT, float* wn, int K, int D, void* stream) {
     if (!W || !WT || !wn || K < 1 || D < 1) return CRK_ERR_ARG;
     k_vq_prepare<<<cdiv(K, 128), 128, 0, (cudaStream_t)stream>>>(W, WT, wn, K, D);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 int crk_vq_argmin(const float* x, int ldx, const float* W, const float* WT, const float* wn,
@@ -149,8 +196,9 @@ int crk_vq_argmin(const float* x, int ldx, const float* W, const float* WT, cons
         API_TRY(cudaFuncSetAttribute(k_vq_argmin, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
+    TimedLaunch tl(CRK_K_VQ_ARGMIN, (cudaStream_t)stream);
     k_vq_argmin<<<(unsigned)cdivl(F, 64), CRK_THREADS, smem, (cudaStream_t)stream>>>(p);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 long long crk_vq_stats_ws_floats(long long F, int K, int D) {
@@ -172,9 +220,9 @@ int crk_vq_stats(const float* x, int ldx, const long long* idx, float* counts, f
         attr_set = true;
     }
     k_vq_stats<<<nchunk, CRK_THREADS, (size_t)K * 65 * sizeof(float), (cudaStream_t)stream>>>(p);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     k_vq_stats_reduce<<<cdiv(K * 65, 256), 256, 0, (cudaStream_t)stream>>>(ws, nchunk, K, counts, esum);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 int crk_vq_ema(const float* counts, const float* esum, float* ema_size, float* ema_w, float* W,
@@ -185,14 +233,14 @@ int crk_vq_ema(const float* counts, const float* esum, float* ema_size, float* e
     const float keps = (float)((double)K * (double)eps);
     k_vq_ema<<<1, 512, 0, (cudaStream_t)stream>>>(counts, esum, ema_size, ema_w, W, decay, one_m_decay, eps,
                                                    keps, K, D);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 int crk_vq_scatter_grad(const float* g, int ldg, const long long* idx, float* dW, long long F,
                         int K, int D, void* stream) {
     if (!g || !idx || !dW || F < 1 || K < 1 || D < 1) return CRK_ERR_ARG;
     k_vq_scatter_grad<<<(unsigned)cdivl(F * D, 256), 256, 0, (cudaStream_t)stream>>>(g, ldg, idx, dW, F, D);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 
@@ -219,9 +267,9 @@ int crk_masked_loss_fwd(const float* x, int ldx, const float* y, int ldy, float 
     const int Tp = T - (shift < 0 ? -shift : shift);
     const int nblk = loss_blocks((long long)B * Tp * D);
     k_masked_loss_part<<<nblk, CRK_THREADS, 0, (cudaStream_t)stream>>>(p, ws);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     k_finalize<<<1, CRK_THREADS, 0, (cudaStream_t)stream>>>(ws, nblk, 3, out, 2, 2);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 int crk_masked_loss_bwd(const float* x, int ldx, const float* y, int ldy, float yconst,
@@ -234,7 +282,7 @@ int crk_masked_loss_bwd(const float* x, int ldx, const float* y, int ldy, float 
     if (!out || !dx) return CRK_ERR_ARG;
     const long long N = (long long)B * T * D;
     k_masked_loss_bwd<<<(unsigned)cdivl(N, CRK_THREADS), CRK_THREADS, 0, (cudaStream_t)stream>>>(p, out, g_l1, g_mse, dx, lddx);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 
@@ -263,11 +311,11 @@ int crk_stft_loss_fwd(const float* x, int ldx, const float* y, int ldy, int B, i
     const int nblk = loss_blocks(N);
     const size_t smem = (size_t)3 * n_fft * sizeof(float);
     k_stft_loss_part<<<nblk, CRK_THREADS, smem, (cudaStream_t)stream>>>(p, ws);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     k_finalize<<<1, CRK_THREADS, 0, (cudaStream_t)stream>>>(ws, nblk, 2, out, 0, -1);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     k_scale2<<<1, 1, 0, (cudaStream_t)stream>>>(out, 1.0f / (float)N);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 int crk_stft_loss_bwd(const float* x, int ldx, const float* y, int ldy, int B, int T, int D,
@@ -281,14 +329,14 @@ int crk_stft_loss_bwd(const float* x, int ldx, const float* y, int ldy, int B, i
     if (!accumulate) {
         const long long rows = (long long)B * T;
         k_zero_panel<<<(unsigned)cdivl(rows * D, 256), 256, 0, s>>>(dx, lddx, D, rows);
-        API_TRY(cudaGetLastError());
+        API_TRY(launch_check());
     }
     const long long nfr = (long long)B * D * p.M;
     long long nblk = cdivl(nfr, 8);
     if (nblk > 148 * 8) nblk = 148 * 8;
     const size_t smem = (size_t)(3 * n_fft + 16 * p.bins) * sizeof(float);
     k_stft_loss_bwd<<<(unsigned)nblk, CRK_THREADS, smem, s>>>(p, g, scale, dx, lddx);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 
@@ -301,9 +349,9 @@ int crk_ce_fwd(const float* logits, int ldl, const long long* labels, long long 
     if (!logits || !labels || !out || !ws || F < 1 || S < 1) return CRK_ERR_ARG;
     const int nblk = loss_blocks(F * 8);
     k_ce_part<<<nblk, CRK_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, F, S, ignore_index, ws);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     k_finalize<<<1, CRK_THREADS, 0, (cudaStream_t)stream>>>(ws, nblk, 2, out, 1, 1);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 int crk_ce_bwd(const float* logits, int ldl, const long long* labels, long long F, int S,
@@ -311,7 +359,7 @@ int crk_ce_bwd(const float* logits, int ldl, const long long* labels, long long 
                void* stream) {
     if (!logits || !labels || !out || !g || !dlogits || F < 1 || S < 1) return CRK_ERR_ARG;
     k_ce_bwd<<<(unsigned)cdivl(F, CRK_THREADS), CRK_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, labels, F, S, ignore_index, out, g, dlogits, lddl);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 
@@ -325,7 +373,7 @@ int crk_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
     const float step_size = (float)((double)lr / bc1);
     const float bc2_sqrt = (float)sqrt(bc2);
     k_adam<<<(unsigned)cdivl(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_size, bc2_sqrt);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 
@@ -420,7 +468,7 @@ int crk_logmel_fwd(const float* wav, int B, long long n_samples, const float* wi
     float2* spec = reinterpret_cast<float2*>(ws + spec_off);
     const long long total = F * n_fft;
     k_frame_window<<<(unsigned)cdivl(total, 256), 256, 0, s>>>(wav, n_samples, window, n_fft, hop, M, total, frames);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     auto key = std::make_pair(n_fft, F);
     auto& plans = fft_plans();
     auto it = plans.find(key);
@@ -434,7 +482,7 @@ int crk_logmel_fwd(const float* wav, int B, long long n_samples, const float* wi
     if (cufftSetStream(it->second, s) != CUFFT_SUCCESS) return CRK_ERR_CUDA;
     if (cufftExecR2C(it->second, frames, reinterpret_cast<cufftComplex*>(spec)) != CUFFT_SUCCESS) return CRK_ERR_CUDA;
     k_mel<<<(unsigned)cdivl(F, 64), CRK_THREADS, 0, s>>>(spec, bins, mel_basis, n_mels, eps, mean, stdv, F, out);
-    API_TRY(cudaGetLastError());
+    API_TRY(launch_check());
     return CRK_OK;
 }
 

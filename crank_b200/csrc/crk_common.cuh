@@ -30,6 +30,32 @@
 
 namespace crk {
 
+// ---- instrumentation: launch counter + optional per-kernel CUDA-event timing -------------------
+// Every kernel launch of the library bumps the counter (bench.py reports it as gpu_launches).
+// crk_timing_enable(id) makes the launch helpers of kernel family `id` record a cudaEvent pair
+// on the launch stream around each launch; crk_timing_read() synchronises and sums them.
+enum { CRK_K_RESBLOCK_FWD = 1, CRK_K_WGRAD = 2, CRK_K_CONV = 3, CRK_K_BWD_GATE = 4, CRK_K_VQ_ARGMIN = 5, CRK_K_MAX = 8 };
+struct Instr {
+    unsigned long long launches = 0;
+    int enabled_id = 0;
+    static const int kMaxPairs = 8192;
+    cudaEvent_t* ev = nullptr;   // 2*kMaxPairs
+    int npairs = 0;
+};
+inline Instr& instr() { static Instr i; return i; }
+inline cudaError_t launch_check() { ++instr().launches; return cudaGetLastError(); }
+struct TimedLaunch {   // RAII: records events around a launch when timing of `id` is on
+    bool on; cudaStream_t s; int slot;
+    TimedLaunch(int id, cudaStream_t st) : on(false), s(st), slot(0) {
+        Instr& I = instr();
+        if (I.enabled_id == id && I.ev && I.npairs < Instr::kMaxPairs) {
+            on = true; slot = I.npairs++;
+            cudaEventRecord(I.ev[2 * slot], s);
+        }
+    }
+    ~TimedLaunch() { if (on) cudaEventRecord(instr().ev[2 * slot + 1], s); }
+};
+
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long cdivl(long long a, long long b) { return (a + b - 1) / b; }

@@ -155,8 +155,9 @@ inline cudaError_t launch_conv_t(const ConvParams& p, cudaStream_t s) {
         attr_set = true;
     }
     const int tiles = p.B * cdiv(p.T, CRK_TM);
+    TimedLaunch tl(CRK_K_CONV, s);
     k_conv<CPT><<<tiles, CRK_THREADS, conv_smem_bytes(p, CPT), s>>>(p);
-    return cudaGetLastError();
+    return launch_check();
 }
 
 // `cpt` must match the packing of p.W / p.bias (TN = 32*cpt)
@@ -303,8 +304,9 @@ inline cudaError_t launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    TimedLaunch tl(CRK_K_WGRAD, s);
     k_wgrad<CPT><<<grid, CRK_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    return launch_check();
 }
 
 // dW (and db when non-null) of one convolution.  cpt gives the packing of the G columns (TN=32*cpt).
@@ -325,17 +327,17 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
     if (e != cudaSuccess) return e;
     const int n = p.k * p.Rows * TN;
     k_reduce<<<cdiv(n, 256), 256, 0, s>>>(part, w.nchunk, n, dW, 0);
-    e = cudaGetLastError();
+    e = launch_check();
     if (e != cudaSuccess) return e;
     if (db) {
         const long long F = (long long)p.B * p.T;
         const int rows_per_chunk = (int)cdivl(F, colsum_chunks(F));
         const int nch = (int)cdivl(F, rows_per_chunk);
         k_colsum<<<nch, CRK_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part, TN);
-        e = cudaGetLastError();
+        e = launch_check();
         if (e != cudaSuccess) return e;
         k_reduce<<<cdiv(TN, 128), 128, 0, s>>>(part, nch * 2, TN, db, 0);
-        e = cudaGetLastError();
+        e = launch_check();
     }
     return e;
 }

@@ -126,8 +126,9 @@ inline cudaError_t launch_resblock_fwd(const ResFwdParams& p, cudaStream_t s) {
         attr_set = true;
     }
     const int tiles = p.B * cdiv(p.T, CRK_TM);
+    TimedLaunch tl(CRK_K_RESBLOCK_FWD, s);
     k_resblock_fwd<<<tiles, CRK_THREADS, resblock_fwd_smem(p.k, p.dil, p.CaPad), s>>>(p);
-    return cudaGetLastError();
+    return launch_check();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -205,8 +206,9 @@ inline cudaError_t launch_resblock_bwd_gate(const ResBwdGateParams& p, cudaStrea
         attr_set = true;
     }
     const int tiles = p.B * cdiv(p.T, CRK_TM);
+    TimedLaunch tl(CRK_K_BWD_GATE, s);
     k_resblock_bwd_gate<<<tiles, CRK_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    return launch_check();
 }
 
 }  // namespace crk

@@ -109,14 +109,14 @@ inline cudaError_t launch_weightnorm(const DescTable& tab, const float* theta, f
     int maxc = 1;
     for (int i = 0; i < tab.n; ++i) maxc = tab.d[i].cout > maxc ? tab.d[i].cout : maxc;
     k_weightnorm_fwd<<<dim3(maxc, tab.n), 128, 0, s>>>(tab, theta, weff);
-    return cudaGetLastError();
+    return launch_check();
 }
 inline cudaError_t launch_weightnorm_bwd(const DescTable& tab, const float* theta, const float* gweff,
                                          float* gtheta, cudaStream_t s) {
     int maxc = 1;
     for (int i = 0; i < tab.n; ++i) maxc = tab.d[i].cout > maxc ? tab.d[i].cout : maxc;
     k_weightnorm_bwd<<<dim3(maxc, tab.n), 128, 0, s>>>(tab, theta, gweff, gtheta);
-    return cudaGetLastError();
+    return launch_check();
 }
 
 // ---- layout builder ---------------------------------------------------------------------------

@@ -32,4 +32,7 @@ class FusedAdam(torch.optim.Optimizer):
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 ops.adam_step(p.data, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), b1, b2,
                               group["eps"], st["step"])
+                # the kernel wrote through the raw pointer: bump the autograd version so that the
+                # weight-norm caches keyed on it (parallel_wavegan.models) are invalidated
+                torch.autograd.graph.increment_version(p)
         return loss

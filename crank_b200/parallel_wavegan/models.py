@@ -122,6 +122,19 @@ class _PackedConvNet(torch.nn.Module):
                 if k.startswith(prefix) and k not in own:
                     unexpected_keys.append(k)
 
+    def named_conv_grads(self):
+        """{reference parameter key: gradient view} sliced out of theta.grad (tests / inspection)."""
+        out = {}
+        if self.theta.grad is None:
+            return out
+        gr = self.theta.grad
+        for name, d in zip(self._names, self._descs):
+            out[name + ".weight_g"] = gr[d.g_off : d.g_off + d.cout].view(d.cout, 1, 1)
+            out[name + ".weight_v"] = gr[d.v_off : d.v_off + d.cout * d.cin * d.k].view(d.cout, d.cin, d.k)
+            if d.b_off >= 0:
+                out[name + ".bias"] = gr[d.b_off : d.b_off + d.cout]
+        return out
+
     def apply_weight_norm(self):
         self._weight_norm_removed = False
 

@@ -35,6 +35,20 @@ const char* crk_strerror(int code);
 const char* crk_last_cuda_error(void);
 int crk_version(void);
 
+/* instrumentation: number of kernels the library has launched in this process; optional CUDA-event
+ * timing of one kernel family (ids: 1 resblock_fwd, 2 wgrad, 3 conv, 4 resblock_bwd_gate, 5 vq_argmin;
+ * 0 disables).  crk_timing_read synchronises the device and returns (#launches, total ms) since enable. */
+unsigned long long crk_launch_count(void);
+int crk_timing_enable(int kernel_id);
+int crk_timing_read(int* count, float* total_ms);
+
+/* tcgen05 probe: single-CTA TF32 GEMM through the tensor-core kernels' operand layout / descriptors /
+ * TMEM path.  mode 0: D[m][n] = sum_k A[row_shift+m][k]*B[n][k]  (K-major operands, any row shift);
+ * mode 1: D[m][n] = sum_f A[f][m]*B[f][n]  (MN-major operands, K = #frames).  M = 128, N in {64,128},
+ * K % 8 == 0; split != 0 -> 3xTF32 error-compensated product.  D is (128, N) row-major. */
+int crk_tc_probe(const float* A, int lda, int rowsA, const float* B, int ldb, int rowsB, float* D, int N,
+                 int K, int row_shift, int mode, int split, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * WaveNet stack = parallel_wavegan.models.ParallelWaveGANGenerator (upsample off) and
  * ResidualParallelWaveGANDiscriminator.   Replaces: crank/net/module/vqvae2.py:236-273 (encoders /
