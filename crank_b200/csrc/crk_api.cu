@@ -45,6 +45,12 @@ const char* crk_strerror(int code) {
 const char* crk_last_cuda_error(void) { return g_cuda_err; }
 int crk_version(void) { return 100; }
 
+int crk_set_precision(int mode) {
+    if (mode < CRK_PREC_FP32 || mode > CRK_PREC_TF32) return CRK_ERR_ARG;
+    precision_mode() = mode;
+    return CRK_OK;
+}
+int crk_get_precision(void) { return precision_mode(); }
 unsigned long long crk_launch_count(void) { return instr().launches; }
 int crk_timing_enable(int kernel_id) {
     Instr& I = instr();
@@ -77,13 +83,13 @@ int crk_timing_read(int* count, float* total_ms) {
 int crk_tc_probe(const float* A, int lda, int rowsA, const float* B, int ldb, int rowsB, float* D, int N,
                  int K, int row_shift, int mode, int split, void* stream) {
     if (!A || !B || !D || (N != 64 && N != 128) || K < 8 || (K % 8) != 0 || row_shift < 0) return CRK_ERR_ARG;
-    if (mode == 0 && (rowsA < 128 + row_shift || rowsB < N)) return CRK_ERR_ARG;
-    if (mode == 1 && (rowsA < K || rowsB < K)) return CRK_ERR_ARG;
+    if ((mode & 1) == 0 && (rowsA < 128 + row_shift || rowsB < N)) return CRK_ERR_ARG;
+    if ((mode & 1) == 1 && (rowsA < K || rowsB < K)) return CRK_ERR_ARG;
     TcProbeParams p;
     p.A = A; p.lda = lda; p.rowsA = rowsA; p.B = B; p.ldb = ldb; p.rowsB = rowsB; p.D = D;
-    p.N = N; p.K = K; p.row_shift = row_shift; p.mode = mode; p.split = split;
-    const int colsA = mode == 0 ? K : 128, colsB = mode == 0 ? K : N;
-    const size_t smem = (size_t)2 * ((colsA / 4) * tc::chunk_stride_bytes(rowsA) + (colsB / 4) * tc::chunk_stride_bytes(rowsB));
+    p.N = N; p.K = K; p.row_shift = row_shift; p.mode = mode & 1; p.split = split; p.variant = mode >> 1;
+    const int colsA = p.mode == 0 ? K : 128, colsB = p.mode == 0 ? K : N;
+    const size_t smem = (size_t)(split ? 2 : 1) * ((colsA / 4) * tc::chunk_stride_bytes(rowsA) + (colsB / 4) * tc::chunk_stride_bytes(rowsB));
     if (smem > 200 * 1024) return CRK_ERR_UNSUPPORTED;
     API_TRY(cudaFuncSetAttribute(k_tc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     k_tc_probe<<<1, 128, smem, (cudaStream_t)stream>>>(p);

@@ -56,6 +56,11 @@ struct TimedLaunch {   // RAII: records events around a launch when timing of `i
     ~TimedLaunch() { if (on) cudaEventRecord(instr().ev[2 * slot + 1], s); }
 };
 
+// arithmetic of the dense conv contractions: fp32 CUDA cores, 3xTF32 (error-compensated, ~fp32
+// accuracy) or plain TF32 on the tcgen05 tensor cores.  Process-wide; set by crk_set_precision().
+enum { CRK_PREC_FP32 = 0, CRK_PREC_TF32X3 = 1, CRK_PREC_TF32 = 2 };
+inline int& precision_mode() { static int m = CRK_PREC_FP32; return m; }
+
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long cdivl(long long a, long long b) { return (a + b - 1) / b; }

@@ -7,6 +7,7 @@
 #include "crk_common.cuh"
 #include "crk_conv.cuh"
 #include "crk_resblock.cuh"
+#include "crk_resblock_tc.cuh"
 
 namespace crk {
 
@@ -59,6 +60,15 @@ __global__ void __launch_bounds__(128) k_weightnorm_fwd(const DescTable tab, con
         weff[d.w_off + ((size_t)j * d.cin_pad + ci) * d.ldw + pc] = w;
         if (d.wt_off >= 0)
             weff[d.wt_off + ((size_t)(d.k - 1 - j) * d.wt_rows + pc) * d.ldwt + ci] = w;
+        if (d.tc_off >= 0) {
+            // tensor-core B operand of tap j: [K chunk of 4][n = packed column, 129 rows][4], hi then lo
+            const int half = tc_blob_half(d.tc_kpad, d.ldw);
+            float hi, lo;
+            tc::split_tf32(w, hi, lo);
+            const size_t o = (size_t)d.tc_off + (size_t)j * 2 * half + (size_t)(ci >> 2) * tc::chunk_rows(d.ldw) * 4 + pc * 4 + (ci & 3);
+            weff[o] = hi;
+            weff[o + half] = lo;
+        }
     }
     if (threadIdx.x == 0 && d.b_off >= 0) weff[d.bias_off + pc] = theta[d.b_off + co];
 }
@@ -125,7 +135,8 @@ struct LayoutBuilder {
     long long theta = 0, weff = 0;
     LayoutBuilder() { tab.n = 0; }
     // returns index; share >= 0: reuse the packed W/bias/WT slots of conv `share` (out|skip pair)
-    int add(int cout, int cin, int k, bool bias, int perm, int ldw, int wt_rows, int ldwt, int share = -1) {
+    int add(int cout, int cin, int k, bool bias, int perm, int ldw, int wt_rows, int ldwt, int share = -1,
+            bool tcpack = false) {
         crk_conv_desc& d = tab.d[tab.n];
         d.cout = cout; d.cin = cin; d.k = k;
         d.g_off = (int)theta; theta += cout;
@@ -133,12 +144,15 @@ struct LayoutBuilder {
         if (bias) { d.b_off = (int)theta; theta += cout; } else d.b_off = -1;
         d.cin_pad = round_up(cin, 4); d.ldw = ldw; d.perm = perm;
         d.wt_rows = wt_rows; d.ldwt = ldwt;
+        d.tc_off = -1; d.tc_kpad = round_up(cin, 8);
         if (share >= 0) {
             d.w_off = tab.d[share].w_off; d.bias_off = tab.d[share].bias_off; d.wt_off = tab.d[share].wt_off;
+            d.tc_off = tab.d[share].tc_off;
         } else {
             d.w_off = (int)weff; weff += (long long)k * d.cin_pad * ldw;
             d.bias_off = (int)weff; weff += ldw;
             d.wt_off = (int)weff; weff += (long long)k * wt_rows * ldwt;
+            if (tcpack) { d.tc_off = (int)weff; weff += (long long)k * 2 * tc_blob_half(d.tc_kpad, ldw); }
         }
         return tab.n++;
     }
@@ -162,9 +176,9 @@ inline int wavenet_layout(const crk_wavenet_cfg* c, WavenetLayout* L) {
     LayoutBuilder b;
     L->first = b.add(64, c->in_ch, 1, true, 0, 64, 64, 32 * cpt_for(c->in_ch));
     for (int l = 0; l < c->layers; ++l) {
-        L->conv[l] = b.add(128, 64, c->kernel_size, true, 1, 128, 128, 64);
-        L->aux[l] = c->aux_ch > 0 ? b.add(128, c->aux_ch, 1, false, 1, 128, 128, 32 * cpt_for(c->aux_ch)) : -1;
-        L->out[l] = b.add(64, 64, 1, true, 2, 128, 128, 64);
+        L->conv[l] = b.add(128, 64, c->kernel_size, true, 1, 128, 128, 64, -1, true);
+        L->aux[l] = c->aux_ch > 0 ? b.add(128, c->aux_ch, 1, false, 1, 128, 128, 32 * cpt_for(c->aux_ch), -1, true) : -1;
+        L->out[l] = b.add(64, 64, 1, true, 2, 128, 128, 64, -1, true);
         L->skip[l] = b.add(64, 64, 1, true, 3, 128, 128, 64, L->out[l]);
     }
     L->last1 = b.add(64, 64, 1, true, 0, 64, 64, 64);
@@ -251,7 +265,19 @@ inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float*
         p.dropmul = dropmul ? dropmul + (long long)l * F * 64 : nullptr;
         p.TaSb = act + A.tasb + (long long)l * F * 128;
         p.B = B; p.T = T; p.k = c->kernel_size; p.dil = dil; p.padl = wn_padl(c, dil);
-        CRK_TRY(launch_resblock_fwd(p, s));
+        const int mode = precision_mode();
+        if (mode == CRK_PREC_FP32 || (c->kernel_size - 1) * dil > 16) {
+            CRK_TRY(launch_resblock_fwd(p, s));
+        } else {
+            ResFwdTcParams q;
+            q.p = p;
+            q.WcTc = weff + L.tab.d[L.conv[l]].tc_off;
+            q.WosTc = weff + L.tab.d[L.out[l]].tc_off;
+            q.WaTc = c->aux_ch > 0 ? weff + L.tab.d[L.aux[l]].tc_off : nullptr;
+            q.KaPad = c->aux_ch > 0 ? L.tab.d[L.aux[l]].tc_kpad : 0;
+            if (mode == CRK_PREC_TF32X3) CRK_TRY(launch_resblock_fwd_tc<true>(q, s));
+            else CRK_TRY(launch_resblock_fwd_tc<false>(q, s));
+        }
     }
     const float hscale = sqrtf(1.0f / (float)c->layers);
     {

@@ -17,7 +17,7 @@ struct TcProbeParams {
     const float* B; int ldb; int rowsB;
     float* D;
     int N, K;          // mode 0: K = reduction (multiple of 8) ; mode 1: K = #frames (multiple of 8)
-    int row_shift, mode, split;
+    int row_shift, mode, split, variant;   // variant bit0: swap LBO/SBO of MN-major descriptors (diagnostic)
 };
 
 // stage src[rows][cols] (row-major, ld) into chunk-major smem tiles (hi and optionally lo)
@@ -45,9 +45,9 @@ __global__ void __launch_bounds__(128) k_tc_probe(const TcProbeParams p) {
     const int colsB = p.mode == 0 ? p.K : p.N;
     const int csA = tc::chunk_stride_bytes(p.rowsA) / 4, csB = tc::chunk_stride_bytes(p.rowsB) / 4;
     float* a_hi = smem;
-    float* a_lo = a_hi + (colsA / 4) * csA;
+    float* a_lo = a_hi + (p.split ? (colsA / 4) * csA : 0);
     float* b_hi = a_lo + (colsA / 4) * csA;
-    float* b_lo = b_hi + (colsB / 4) * csB;
+    float* b_lo = b_hi + (p.split ? (colsB / 4) * csB : 0);
     const int warp = threadIdx.x >> 5;
 
     tc_stage(a_hi, p.split ? a_lo : nullptr, p.A, p.lda, p.rowsA, colsA, csA);
@@ -79,8 +79,13 @@ __global__ void __launch_bounds__(128) k_tc_probe(const TcProbeParams p) {
                     db = tc::make_smem_desc(bs + (k0 / 4) * csBb, csBb, 128);
                 } else {
                     // MN-major: rows = K index (frames, 8 per MMA, 16 B apart); M/N chunks of 4 are CS apart (SBO)
-                    da = tc::make_smem_desc(as + k0 * 16, 128, csAb);
-                    db = tc::make_smem_desc(bs + k0 * 16, 128, csBb);
+                    if (p.variant & 1) {
+                        da = tc::make_smem_desc(as + k0 * 16, csAb, 128);
+                        db = tc::make_smem_desc(bs + k0 * 16, csBb, 128);
+                    } else {
+                        da = tc::make_smem_desc(as + k0 * 16, 128, csAb);
+                        db = tc::make_smem_desc(bs + k0 * 16, 128, csBb);
+                    }
                 }
                 tc::umma_tf32(tmem, da, db, idesc, acc);
                 acc = 1;

@@ -37,7 +37,7 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("g_off", i32), ("v_off", i32), ("b_off", i32), ("cout", i32), ("cin", i32), ("k", i32),
         ("w_off", i32), ("bias_off", i32), ("cin_pad", i32), ("ldw", i32), ("perm", i32),
-        ("wt_off", i32), ("wt_rows", i32), ("ldwt", i32),
+        ("wt_off", i32), ("wt_rows", i32), ("ldwt", i32), ("tc_off", i32), ("tc_kpad", i32),
     ]
 
 
@@ -51,6 +51,8 @@ SIGNATURES = {
     "crk_strerror": (C.c_char_p, [i32]),
     "crk_last_cuda_error": (C.c_char_p, []),
     "crk_version": (i32, []),
+    "crk_set_precision": (i32, [i32]),
+    "crk_get_precision": (i32, []),
     "crk_launch_count": (C.c_ulonglong, []),
     "crk_timing_enable": (i32, [i32]),
     "crk_timing_read": (i32, [C.POINTER(i32), C.POINTER(f32)]),
@@ -164,3 +166,17 @@ def describe_convstack(cfg):
     check(lib().crk_convstack_describe(C.byref(cfg), descs, C.byref(n), C.byref(th), C.byref(we)),
           "crk_convstack_describe")
     return [descs[i] for i in range(n.value)], th.value, we.value
+
+
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+
+
+def set_precision(mode):
+    """Arithmetic of the dense conv contractions: "fp32" (CUDA cores), "tf32x3" (tcgen05, error-compensated,
+    ~fp32 accuracy -- the parity mode) or "tf32" (tcgen05, fast mode).  Process-wide."""
+    check(lib().crk_set_precision(PRECISIONS[mode] if isinstance(mode, str) else int(mode)), "crk_set_precision")
+
+
+def get_precision():
+    inv = {v: k for k, v in PRECISIONS.items()}
+    return inv[lib().crk_get_precision()]

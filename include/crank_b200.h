@@ -35,6 +35,11 @@ const char* crk_strerror(int code);
 const char* crk_last_cuda_error(void);
 int crk_version(void);
 
+/* arithmetic of the dense conv contractions (process-wide): 0 = fp32 CUDA cores, 1 = 3xTF32 on the
+ * tcgen05 tensor cores (error-compensated, ~fp32 accuracy: the parity mode), 2 = plain TF32 (fast mode). */
+int crk_set_precision(int mode);
+int crk_get_precision(void);
+
 /* instrumentation: number of kernels the library has launched in this process; optional CUDA-event
  * timing of one kernel family (ids: 1 resblock_fwd, 2 wgrad, 3 conv, 4 resblock_bwd_gate, 5 vq_argmin;
  * 0 disables).  crk_timing_read synchronises the device and returns (#launches, total ms) since enable. */
@@ -73,6 +78,8 @@ typedef struct {
     int w_off, bias_off;         /* offsets into the packed effective-weight buffer ("weff") */
     int cin_pad, ldw, perm;      /* fwd packing  W[j][cin_pad][ldw], column permutation id */
     int wt_off, wt_rows, ldwt;   /* transposed, tap-flipped copy for dgrad; wt_off < 0: none */
+    int tc_off, tc_kpad;         /* tensor-core operand blobs (chunk-major, tf32 hi|lo split) per tap;
+                                    tc_off < 0: none.  tc_kpad = K rounded up to 8 */
 } crk_conv_desc;
 
 #define CRK_MAX_CONVS 64

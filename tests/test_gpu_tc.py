@@ -41,3 +41,67 @@ def test_tc_probe_mn_major_wgrad_style(N, frames, split):
     assert not torch.isnan(D).any(), "tcgen05 pipeline did not complete (mbarrier timeout)"
     err = ((D - ref).abs().max() / ref.abs().max()).item()
     assert err < (2e-6 if split else 3e-3), err
+
+
+@pytest.fixture
+def precision():
+    from crank_b200 import lib as L
+
+    def _set(mode):
+        L.set_precision(mode)
+
+    yield _set
+    L.set_precision("fp32")
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 1e-4), ("tf32", 2e-2)])
+@pytest.mark.parametrize(
+    "in_ch,out_ch,aux,k,layers,stacks,B,T",
+    [
+        (80, 64, 0, 5, 8, 4, 3, 300),     # encoder 0: k5, dilations 1,2
+        (64, 64, 0, 3, 6, 3, 2, 130),     # encoder 1 / decoder 1
+        (128, 80, 34, 5, 8, 4, 2, 200),   # decoder 0 with aux conditioning
+        (80, 64, 0, 3, 2, 1, 1, 17),      # T smaller than a tile
+    ],
+)
+def test_tensor_core_forward_matches_oracle(precision, mode, tol, in_ch, out_ch, aux, k, layers, stacks, B, T):
+    from tests.test_gpu_kernels import _pair_generator
+    from tests.util import rel_err
+
+    o, p = _pair_generator(in_ch, out_ch, aux, k, layers, stacks, False)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, in_ch, T, generator=g)
+    c = torch.randn(B, aux, T, generator=g) if aux > 0 else None
+    with torch.no_grad():
+        yo = o(x, c)
+    precision(mode)
+    with torch.no_grad():
+        yp = p(x.cuda(), c.cuda() if c is not None else None)
+    assert not torch.isnan(yp).any(), "tcgen05 pipeline timed out (poisoned output)"
+    e = rel_err(yp, yo)
+    print(f"{mode}: forward rel err {e:.2e}")
+    assert e <= tol, e
+
+
+def test_tensor_core_forward_backward_through_saved_gates(precision):
+    """forward on tcgen05 (3xTF32) + fp32 backward kernels: gradients must still match the oracle."""
+    from tests.test_gpu_kernels import _pair_generator
+    from tests.util import assert_close, compare_conv_grads
+
+    o, p = _pair_generator(128, 80, 34, 5, 8, 4, False)
+    g = torch.Generator().manual_seed(2)
+    B, T = 2, 150
+    x = torch.randn(B, 128, T, generator=g)
+    c = torch.randn(B, 34, T, generator=g)
+    xo, co = x.clone().requires_grad_(True), c.clone().requires_grad_(True)
+    yo = o(xo, co)
+    precision("tf32x3")
+    xp, cp = x.cuda().requires_grad_(True), c.cuda().requires_grad_(True)
+    yp = p(xp, cp)
+    dy = torch.randn(yo.shape, generator=g)
+    yo.backward(dy)
+    yp.backward(dy.cuda())
+    assert_close(yp, yo, 1e-4, "fwd")
+    assert_close(xp.grad, xo.grad, 1e-4, "dx")
+    assert_close(cp.grad, co.grad, 1e-4, "dc")
+    compare_conv_grads(p, o, 1e-4, "stack (tc fwd)")
