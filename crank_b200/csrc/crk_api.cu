@@ -51,6 +51,10 @@ int crk_set_precision(int mode) {
     return CRK_OK;
 }
 int crk_get_precision(void) { return precision_mode(); }
+int crk_debug_timestamps(long long* device_buffer) {
+    API_TRY(cudaMemcpyToSymbol(g_crk_dbg, &device_buffer, sizeof(device_buffer)));
+    return CRK_OK;
+}
 unsigned long long crk_launch_count(void) { return instr().launches; }
 int crk_timing_enable(int kernel_id) {
     Instr& I = instr();

@@ -240,28 +240,62 @@ __global__ void __launch_bounds__(CRK_THREADS) k_wgrad(const WgradParams p) {
     }
 }
 
-// out[e] (+)= sum_{chunk} part[chunk][e]   (fixed order => deterministic)
-__global__ void k_reduce(const float* __restrict__ part, int nchunk, int n, float* __restrict__ out,
-                         int accumulate) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    float s = 0.f;
-    for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * n + e];
-    if (accumulate) s += out[e];
-    out[e] = s;
+// out[e] (+)= sum_{chunk} part[chunk][e]   (fixed order => deterministic).  block = (32 x 8): each
+// thread owns 4 consecutive outputs (float4) and every 8th chunk, so 8x more loads are in flight than
+// a one-thread-per-output loop; the 8 partial sums are combined through shared memory in fixed order.
+__global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ part, int nchunk, int n,
+                                                float* __restrict__ out, int accumulate) {
+    __shared__ float4 red[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int e = (blockIdx.x * 32 + tx) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < n) {
+        if (((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(part) & 15) == 0)) {
+            for (int c = ty; c < nchunk; c += 8) {
+                const float4 v = *reinterpret_cast<const float4*>(part + (size_t)c * n + e);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+        } else {
+            for (int c = ty; c < nchunk; c += 8) {
+                const float* q = part + (size_t)c * n + e;
+                s.x += q[0];
+                if (e + 1 < n) s.y += q[1];
+                if (e + 2 < n) s.z += q[2];
+                if (e + 3 < n) s.w += q[3];
+            }
+        }
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && e < n) {
+        float4 t = red[0][tx];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { t.x += red[i][tx].x; t.y += red[i][tx].y; t.z += red[i][tx].z; t.w += red[i][tx].w; }
+        float r4[4] = {t.x, t.y, t.z, t.w};
+        for (int i = 0; i < 4 && e + i < n; ++i) out[e + i] = accumulate ? out[e + i] + r4[i] : r4[i];
+    }
 }
 
-// per-chunk column sums: part[chunk*2 + g][n],  block = 256 threads = 2 row groups x 128 columns
+// per-chunk column sums: part[chunk*2 + g][n],  block = 256 threads = 2 row groups x 128 columns;
+// 4 independent accumulators per thread keep 4 loads in flight
 __global__ void __launch_bounds__(CRK_THREADS) k_colsum(const float* __restrict__ G, int ldg, int N,
                                                          long long F, int rows_per_chunk,
                                                          float* __restrict__ part, int TN) {
     const int n = threadIdx.x & 127, g = threadIdx.x >> 7;
     const long long beg = (long long)blockIdx.x * rows_per_chunk;
     const long long end = min(F, beg + rows_per_chunk);
-    float s = 0.f;
-    if (n < N)
-        for (long long r = beg + g; r < end; r += 2) s += __ldg(G + r * ldg + n);
-    if (n < TN) part[((size_t)blockIdx.x * 2 + g) * TN + n] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (n < N) {
+        long long r = beg + g;
+        for (; r + 6 < end; r += 8) {
+            s0 += __ldg(G + r * ldg + n);
+            s1 += __ldg(G + (r + 2) * ldg + n);
+            s2 += __ldg(G + (r + 4) * ldg + n);
+            s3 += __ldg(G + (r + 6) * ldg + n);
+        }
+        for (; r < end; r += 2) s0 += __ldg(G + r * ldg + n);
+    }
+    if (n < TN) part[((size_t)blockIdx.x * 2 + g) * TN + n] = (s0 + s1) + (s2 + s3);
 }
 
 // Work-partition policy of wgrad: number of per-chunk partials so that the (chunk, tap, rowblock)
@@ -281,8 +315,8 @@ inline WgradWork wgrad_work(int B, int T, int k, int rows) {
     return w;
 }
 inline int colsum_chunks(long long F) {
-    long long n = cdivl(F, 256);
-    if (n > 148) n = 148;
+    long long n = cdivl(F, 64);
+    if (n > 148 * 4) n = 148 * 4;
     if (n < 1) n = 1;
     return (int)n;
 }
@@ -292,6 +326,10 @@ inline size_t wgrad_part_floats(int B, int T, int k, int rows, int tn) {
     WgradWork w = wgrad_work(B, T, k, rows);
     size_t a = (size_t)w.nchunk * k * rows * tn;
     size_t b = (size_t)colsum_chunks((long long)B * T) * 2 * tn;
+    // tensor-core wgrad policy (crk_wgrad_tc.cuh): up to 148 chunks of 64-frame tiles
+    const int ntiles64 = B * cdiv(T, 64);
+    size_t c = (size_t)(ntiles64 < 148 ? ntiles64 : 148) * k * rows * tn;
+    a = a > c ? a : c;
     return a > b ? a : b;
 }
 
@@ -309,24 +347,31 @@ inline cudaError_t launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t 
     return launch_check();
 }
 
+// tensor-core path (defined in crk_wgrad_tc.cuh): returns true when it handled the partials
+bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err);
+
 // dW (and db when non-null) of one convolution.  cpt gives the packing of the G columns (TN=32*cpt).
 inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, float* part,
                               cudaStream_t s) {
-    const WgradWork w = wgrad_work(p.B, p.T, p.k, p.Rows);
     const int TN = 32 * cpt;
     p.part = part;
-    p.tiles_per_chunk = w.tiles_per_chunk;
-    dim3 grid(w.nchunk, p.k, cdiv(p.Rows, 64));
-    cudaError_t e;
-    switch (cpt) {
-        case 1: e = launch_wgrad_t<1>(p, grid, s); break;
-        case 2: e = launch_wgrad_t<2>(p, grid, s); break;
-        case 3: e = launch_wgrad_t<3>(p, grid, s); break;
-        default: e = launch_wgrad_t<4>(p, grid, s); break;
+    cudaError_t e = cudaSuccess;
+    int nchunk = 0;
+    if (!wgrad_tc_try(p, TN, part, s, &nchunk, &e)) {
+        const WgradWork w = wgrad_work(p.B, p.T, p.k, p.Rows);
+        nchunk = w.nchunk;
+        p.tiles_per_chunk = w.tiles_per_chunk;
+        dim3 grid(w.nchunk, p.k, cdiv(p.Rows, 64));
+        switch (cpt) {
+            case 1: e = launch_wgrad_t<1>(p, grid, s); break;
+            case 2: e = launch_wgrad_t<2>(p, grid, s); break;
+            case 3: e = launch_wgrad_t<3>(p, grid, s); break;
+            default: e = launch_wgrad_t<4>(p, grid, s); break;
+        }
     }
     if (e != cudaSuccess) return e;
     const int n = p.k * p.Rows * TN;
-    k_reduce<<<cdiv(n, 256), 256, 0, s>>>(part, w.nchunk, n, dW, 0);
+    k_reduce<<<cdiv(n, 128), 256, 0, s>>>(part, nchunk, n, dW, 0);
     e = launch_check();
     if (e != cudaSuccess) return e;
     if (db) {
@@ -336,7 +381,7 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
         k_colsum<<<nch, CRK_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part, TN);
         e = launch_check();
         if (e != cudaSuccess) return e;
-        k_reduce<<<cdiv(TN, 128), 128, 0, s>>>(part, nch * 2, TN, db, 0);
+        k_reduce<<<cdiv(TN, 128), 256, 0, s>>>(part, nch * 2, TN, db, 0);
         e = launch_check();
     }
     return e;

@@ -1,0 +1,275 @@
+// crank-b200: generic channels-last dilated conv / dgrad on tcgen05 (K-major TF32 / 3xTF32 UMMA).
+//
+// Tensor-core version of k_conv (crk_conv.cuh), same ConvParams contract (prologue / epilogue
+// options), used for: dgrad of the gated conv (X = dg, K = 128, N = 64, k taps), the plain
+// Conv1d+LeakyReLU stacks (speaker classifier C, SPKRADV; crank/bin/train.py:78-89,
+// crank/net/module/spkradv.py:49-60) forward and dgrad, and the 1x1 convs of the WaveNet stacks.
+//   CTA = 128 frames of one utterance;  acc[128 x Npad] (TMEM) += X[j*dil + rows][seg] . W_{j,seg}^T
+// over (tap j, 64-channel K segment) steps; the weight blobs stream through a 2-slot smem ring while
+// the previous step's MMAs run; the A tile (with halo) is staged once, chunk-major (crk_tc.cuh).
+#pragma once
+#include "crk_common.cuh"
+#include "crk_conv.cuh"
+#include "crk_resblock_tc.cuh"
+#include "crk_tc.cuh"
+
+namespace crk {
+
+struct ConvTcParams {
+    ConvParams p;
+    const float* Wtc;     // per tap: hi [Kpad/4][chunk_rows(Npad)][4] | lo [same]
+    int Kpad, Npad;       // K rounded up to 8, UMMA N (multiple of 16, <= 128)
+};
+
+template <bool SPLIT>
+__device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_floats, const ConvParams& p, int Kpad,
+                                                 int b, int tstart, int rows) {
+    const int c4n = Kpad >> 2;
+    const int total = rows * c4n;
+    const bool vec = ((p.ldx & 3) == 0) && ((p.Cin & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
+                     (p.xmul == nullptr || (((p.ldxmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.xmul) & 15) == 0)));
+    constexpr int U = 4;
+    for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
+        float4 v[U], m[U];
+        int off[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + u * blockDim.x;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+            off[u] = -1;
+            if (idx < total) {
+                const int r = idx / c4n, c4 = idx - r * c4n;
+                off[u] = c4 * cs_floats + r * 4;
+                const int tt = tstart + r;
+                const int c = c4 * 4;
+                if (tt >= 0 && tt < p.T && c < p.Cin) {
+                    const size_t row = (size_t)b * p.T + tt;
+                    if (vec) {
+                        v[u] = __ldg(reinterpret_cast<const float4*>(p.X + row * p.ldx) + c4);
+                        if (p.xmul) m[u] = __ldg(reinterpret_cast<const float4*>(p.xmul + row * p.ldxmul) + c4);
+                    } else {
+                        const float* sp = p.X + row * p.ldx + c;
+                        v[u].x = __ldg(sp);
+                        v[u].y = c + 1 < p.Cin ? __ldg(sp + 1) : 0.f;
+                        v[u].z = c + 2 < p.Cin ? __ldg(sp + 2) : 0.f;
+                        v[u].w = c + 3 < p.Cin ? __ldg(sp + 3) : 0.f;
+                        if (p.xmul) {
+                            const float* ms = p.xmul + row * p.ldxmul + c;
+                            m[u].x = __ldg(ms);
+                            m[u].y = c + 1 < p.Cin ? __ldg(ms + 1) : 0.f;
+                            m[u].z = c + 2 < p.Cin ? __ldg(ms + 2) : 0.f;
+                            m[u].w = c + 3 < p.Cin ? __ldg(ms + 3) : 0.f;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (off[u] < 0) continue;
+            float4 x;
+            x.x = apply_act(v[u].x * p.pro_scale, p.pro_act, p.pro_slope) * m[u].x;
+            x.y = apply_act(v[u].y * p.pro_scale, p.pro_act, p.pro_slope) * m[u].y;
+            x.z = apply_act(v[u].z * p.pro_scale, p.pro_act, p.pro_slope) * m[u].z;
+            x.w = apply_act(v[u].w * p.pro_scale, p.pro_act, p.pro_slope) * m[u].w;
+            if (SPLIT) {
+                float4 h, l;
+                tc::split_tf32(x.x, h.x, l.x); tc::split_tf32(x.y, h.y, l.y);
+                tc::split_tf32(x.z, h.z, l.z); tc::split_tf32(x.w, h.w, l.w);
+                *reinterpret_cast<float4*>(hi + off[u]) = h;
+                *reinterpret_cast<float4*>(lo + off[u]) = l;
+            } else {
+                *reinterpret_cast<float4*>(hi + off[u]) = x;
+            }
+        }
+    }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 1) k_conv_tc(const ConvTcParams q) {
+    const ConvParams& p = q.p;
+    extern __shared__ float4 crk_smem4[];
+    float* smem = reinterpret_cast<float*>(crk_smem4);
+    __shared__ uint64_t bar_full[2];
+    __shared__ uint64_t bar_free[2];
+    __shared__ uint64_t bar_acc;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int timeout_s;
+
+    const int tiles_per_utt = (p.T + CRK_TC_TM - 1) / CRK_TC_TM;
+    const int b = blockIdx.x / tiles_per_utt;
+    const int t0 = (blockIdx.x - b * tiles_per_utt) * CRK_TC_TM;
+    const int rowsX = CRK_TC_TM + (p.k - 1) * p.dil;
+    const int csx = tc::chunk_rows(rowsX) * 4;                 // floats per A chunk
+    const int kch = q.Kpad >> 2;                               // A / B chunks over the whole K
+    const int csw = tc::chunk_rows(q.Npad) * 4;                // floats per B chunk
+    const int nseg = (q.Kpad + 63) >> 6;                       // 64-channel K segments
+    const int whalf_tap = kch * csw;                           // floats of the hi half of one tap blob
+    const int seg_max = (kch < 16 ? kch : 16) * csw;           // floats of one segment half in a slot
+    float* Xh = smem;
+    float* Xl = Xh + kch * csx;
+    float* ring = Xl + (SPLIT ? kch * csx : 0);
+    float* slot_hi[2] = {ring, ring + (SPLIT ? 2 : 1) * seg_max};
+    float* slot_lo[2] = {ring + seg_max, ring + 3 * seg_max};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nsteps = p.k * nseg;
+
+    // step -> (tap j, K segment sg): TMA bulk copy of that slice of the tap's blob into a ring slot
+    auto produce = [&](int step) {
+        const int j = step / nseg, sg = step - j * nseg;
+        const int ch0 = sg * 16;
+        const int nch = (kch - ch0) < 16 ? (kch - ch0) : 16;
+        const float* blob = q.Wtc + (size_t)j * 2 * whalf_tap + (size_t)ch0 * csw;
+        tc_bulk_blob<SPLIT>(slot_hi[step & 1], slot_lo[step & 1], blob, nch * csw, whalf_tap, &bar_full[step & 1]);
+    };
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
+        tc::mbar_init(&bar_free[0], 1); tc::mbar_init(&bar_free[1], 1);
+        tc::mbar_init(&bar_acc, 1);
+        tc::fence_mbar_init();
+        timeout_s = 0;
+    }
+    if (warp == 1) tc::tmem_alloc<128>(&tmem_base_s);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    bool ok = true;
+    if (threadIdx.x == 0)
+        for (int st = 0; st < 2 && st < nsteps; ++st) produce(st);
+    tc_stage_act_pro<SPLIT>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
+    tc::fence_proxy_async_smem();
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        for (int st = 2; st < nsteps; ++st) {
+            ok &= tc::mbar_wait(&bar_free[st & 1], ((st - 2) >> 1) & 1);
+            produce(st);
+        }
+    } else if (threadIdx.x == 32) {
+        const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
+        const uint32_t xh_s = tc::smem_u32(Xh), xl_s = tc::smem_u32(Xl);
+        uint32_t acc = 0;
+        for (int st = 0; st < nsteps; ++st) {
+            const int j = st / nseg, sg = st - j * nseg;
+            const int ch0 = sg * 16;
+            const int nch = (kch - ch0) < 16 ? (kch - ch0) : 16;
+            ok &= tc::mbar_wait(&bar_full[st & 1], (st >> 1) & 1);
+            tc::tc_fence_after();
+            tc_issue_kmajor<SPLIT>(tmem, xh_s + ch0 * csx * 4, xl_s + ch0 * csx * 4, csx * 4, j * p.dil,
+                                   tc::smem_u32(slot_hi[st & 1]), tc::smem_u32(slot_lo[st & 1]), csw * 4,
+                                   nch * 4, idesc, acc);
+            tc::umma_commit(&bar_free[st & 1]);
+        }
+        tc::umma_commit(&bar_acc);
+    }
+    ok &= tc::mbar_wait(&bar_acc, 0);
+    tc::tc_fence_after();
+    if (!ok) timeout_s = 1;
+
+    // ---- epilogue (same option order as k_conv) ----
+    // TMEM -> registers is thread-per-row; the accumulators are transposed through a padded smem tile
+    // (all pipeline buffers are free: every MMA has completed) so that the global pass is row-coalesced.
+    const int sst = q.Npad | 1;                                 // odd row stride
+    float* S = smem;
+    {
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const int nblk = (q.Npad + 31) >> 5;
+        for (int blk = warp >> 2; blk < nblk; blk += 2) {
+            float v[32];
+            tc::tmem_ld32(tlane + blk * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (blk * 32 + i < q.Npad) S[r * sst + blk * 32 + i] = v[i];
+        }
+    }
+    __syncthreads();
+    {
+        const int nlive = min(CRK_TC_TM, p.T - t0);
+        const size_t row0 = (size_t)b * p.T + t0;
+        const int total = nlive * p.Cout;
+        constexpr int U = 4;      // independent elements per thread per round: their global loads overlap
+        for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * U) {
+            float y[U], mulv[U], rv[U], dv[U], oldv[U];
+            size_t rowv[U];
+            int cov[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * blockDim.x;
+                cov[u] = -1;
+                if (e < total) {
+                    const int rr = e / p.Cout, co = e - rr * p.Cout;
+                    const size_t row = row0 + rr;
+                    cov[u] = co; rowv[u] = row;
+                    y[u] = S[rr * sst + co];
+                    mulv[u] = p.mul_src ? __ldg(p.mul_src + row * p.ldmul + co) : 1.f;
+                    rv[u] = p.R ? __ldg(p.R + row * p.ldr + co) : 0.f;
+                    dv[u] = p.dact_src ? __ldg(p.dact_src + row * p.lddact + co) : 1.f;
+                    oldv[u] = p.accumulate ? p.Y[row * p.ldy + co] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (cov[u] < 0) continue;
+                float v = y[u];
+                if (p.bias) v += __ldg(p.bias + cov[u]);
+                v = apply_act(v, p.epi_act, p.epi_slope);
+                v *= mulv[u];
+                v += p.rscale * rv[u];
+                if (p.dact_src) v *= act_grad(dv[u], p.dact_mode, p.dact_slope);
+                v *= p.out_scale;
+                v += oldv[u];
+                p.Y[rowv[u] * p.ldy + cov[u]] = v;
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (timeout_s && threadIdx.x == 0) p.Y[((size_t)b * p.T + t0) * p.ldy] = __int_as_float(0x7fc00000);
+    if (warp == 1) tc::tmem_dealloc<128>(tmem);
+}
+
+inline size_t conv_tc_smem(const ConvTcParams& q, bool split) {
+    const int rowsX = CRK_TC_TM + (q.p.k - 1) * q.p.dil;
+    const int kch = q.Kpad >> 2;
+    const size_t a = (size_t)kch * tc::chunk_rows(rowsX) * 4;
+    const size_t seg = (size_t)(kch < 16 ? kch : 16) * tc::chunk_rows(q.Npad) * 4;
+    const size_t pipe = (split ? 2 : 1) * a + (split ? 4 : 2) * seg;
+    const size_t stage = (size_t)CRK_TC_TM * (q.Npad | 1);      // epilogue transposition tile
+    return (pipe > stage ? pipe : stage) * sizeof(float);
+}
+inline bool conv_tc_ok(const ConvTcParams& q, bool split) {
+    return q.Wtc != nullptr && q.Npad >= 16 && q.Npad <= 128 && (q.Npad % 16) == 0 && q.Kpad >= 8 && q.Kpad <= 128 &&
+           (q.p.k - 1) * q.p.dil <= 32 && conv_tc_smem(q, split) <= 220 * 1024;
+}
+
+template <bool SPLIT>
+inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_conv_tc<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tiles = q.p.B * cdiv(q.p.T, CRK_TC_TM);
+    TimedLaunch tl(CRK_K_CONV, s);
+    k_conv_tc<SPLIT><<<tiles, 256, conv_tc_smem(q, SPLIT), s>>>(q);
+    return launch_check();
+}
+
+// precision-aware dispatch: tensor cores when enabled and the shape fits, else the fp32 kernel
+inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc, int kpad, int npad, cudaStream_t s) {
+    const int mode = precision_mode();
+    if (mode != CRK_PREC_FP32) {
+        ConvTcParams q;
+        q.p = p; q.Wtc = wtc; q.Kpad = kpad; q.Npad = npad;
+        const bool split = mode == CRK_PREC_TF32X3;
+        if (conv_tc_ok(q, split)) return split ? launch_conv_tc_t<true>(q, s) : launch_conv_tc_t<false>(q, s);
+    }
+    return launch_conv(p, cpt, s);
+}
+
+}  // namespace crk

@@ -8,6 +8,8 @@
 #include "crk_conv.cuh"
 #include "crk_resblock.cuh"
 #include "crk_resblock_tc.cuh"
+#include "crk_conv_tc.cuh"
+#include "crk_wgrad_tc.cuh"
 
 namespace crk {
 
@@ -61,13 +63,18 @@ __global__ void __launch_bounds__(128) k_weightnorm_fwd(const DescTable tab, con
         if (d.wt_off >= 0)
             weff[d.wt_off + ((size_t)(d.k - 1 - j) * d.wt_rows + pc) * d.ldwt + ci] = w;
         if (d.tc_off >= 0) {
-            // tensor-core B operand of tap j: [K chunk of 4][n = packed column, 129 rows][4], hi then lo
-            const int half = tc_blob_half(d.tc_kpad, d.ldw);
             float hi, lo;
             tc::split_tf32(w, hi, lo);
-            const size_t o = (size_t)d.tc_off + (size_t)j * 2 * half + (size_t)(ci >> 2) * tc::chunk_rows(d.ldw) * 4 + pc * 4 + (ci & 3);
+            // forward B operand of tap j: [K chunk (ci/4)][n = packed column][ci%4], hi then lo
+            const int half = tc_blob_half(d.tc_kpad, d.tc_n);
+            const size_t o = (size_t)d.tc_off + (size_t)j * 2 * half + (size_t)(ci >> 2) * tc::chunk_rows(d.tc_n) * 4 + pc * 4 + (ci & 3);
             weff[o] = hi;
             weff[o + half] = lo;
+            // dgrad B operand of flipped tap k-1-j: [K chunk (pc/4)][n = ci][pc%4]
+            const int halft = tc_blob_half(d.tct_kpad, d.tct_n);
+            const size_t ot = (size_t)d.tct_off + (size_t)(d.k - 1 - j) * 2 * halft + (size_t)(pc >> 2) * tc::chunk_rows(d.tct_n) * 4 + ci * 4 + (pc & 3);
+            weff[ot] = hi;
+            weff[ot + halft] = lo;
         }
     }
     if (threadIdx.x == 0 && d.b_off >= 0) weff[d.bias_off + pc] = theta[d.b_off + co];
@@ -135,8 +142,7 @@ struct LayoutBuilder {
     long long theta = 0, weff = 0;
     LayoutBuilder() { tab.n = 0; }
     // returns index; share >= 0: reuse the packed W/bias/WT slots of conv `share` (out|skip pair)
-    int add(int cout, int cin, int k, bool bias, int perm, int ldw, int wt_rows, int ldwt, int share = -1,
-            bool tcpack = false) {
+    int add(int cout, int cin, int k, bool bias, int perm, int ldw, int wt_rows, int ldwt, int share = -1) {
         crk_conv_desc& d = tab.d[tab.n];
         d.cout = cout; d.cin = cin; d.k = k;
         d.g_off = (int)theta; theta += cout;
@@ -144,15 +150,17 @@ struct LayoutBuilder {
         if (bias) { d.b_off = (int)theta; theta += cout; } else d.b_off = -1;
         d.cin_pad = round_up(cin, 4); d.ldw = ldw; d.perm = perm;
         d.wt_rows = wt_rows; d.ldwt = ldwt;
-        d.tc_off = -1; d.tc_kpad = round_up(cin, 8);
+        d.tc_kpad = round_up(cin, 8); d.tc_n = perm != 0 ? 128 : round_up(cout, 16);
+        d.tct_kpad = perm != 0 ? 128 : round_up(cout, 8); d.tct_n = round_up(cin, 16);
         if (share >= 0) {
             d.w_off = tab.d[share].w_off; d.bias_off = tab.d[share].bias_off; d.wt_off = tab.d[share].wt_off;
-            d.tc_off = tab.d[share].tc_off;
+            d.tc_off = tab.d[share].tc_off; d.tct_off = tab.d[share].tct_off;
         } else {
             d.w_off = (int)weff; weff += (long long)k * d.cin_pad * ldw;
             d.bias_off = (int)weff; weff += ldw;
             d.wt_off = (int)weff; weff += (long long)k * wt_rows * ldwt;
-            if (tcpack) { d.tc_off = (int)weff; weff += (long long)k * 2 * tc_blob_half(d.tc_kpad, ldw); }
+            d.tc_off = (int)weff; weff += (long long)k * 2 * tc_blob_half(d.tc_kpad, d.tc_n);
+            d.tct_off = (int)weff; weff += (long long)k * 2 * tc_blob_half(d.tct_kpad, d.tct_n);
         }
         return tab.n++;
     }
@@ -176,9 +184,9 @@ inline int wavenet_layout(const crk_wavenet_cfg* c, WavenetLayout* L) {
     LayoutBuilder b;
     L->first = b.add(64, c->in_ch, 1, true, 0, 64, 64, 32 * cpt_for(c->in_ch));
     for (int l = 0; l < c->layers; ++l) {
-        L->conv[l] = b.add(128, 64, c->kernel_size, true, 1, 128, 128, 64, -1, true);
-        L->aux[l] = c->aux_ch > 0 ? b.add(128, c->aux_ch, 1, false, 1, 128, 128, 32 * cpt_for(c->aux_ch), -1, true) : -1;
-        L->out[l] = b.add(64, 64, 1, true, 2, 128, 128, 64, -1, true);
+        L->conv[l] = b.add(128, 64, c->kernel_size, true, 1, 128, 128, 64);
+        L->aux[l] = c->aux_ch > 0 ? b.add(128, c->aux_ch, 1, false, 1, 128, 128, 32 * cpt_for(c->aux_ch)) : -1;
+        L->out[l] = b.add(64, 64, 1, true, 2, 128, 128, 64);
         L->skip[l] = b.add(64, 64, 1, true, 3, 128, 128, 64, L->out[l]);
     }
     L->last1 = b.add(64, 64, 1, true, 0, 64, 64, 64);
@@ -248,7 +256,7 @@ inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float*
         p.W = weff + d.w_off; p.bias = weff + d.bias_off;
         p.Y = h; p.ldy = 64; p.Cout = 64; p.B = B; p.T = T;
         p.epi_act = c->first_act; p.epi_slope = c->slope;
-        CRK_TRY(launch_conv(p, 2, s));
+        CRK_TRY(conv_dispatch(p, 2, weff + d.tc_off, d.tc_kpad, d.tc_n, s));
     }
     for (int l = 0; l < c->layers; ++l) {
         const int dil = wn_dilation(c, l);
@@ -287,7 +295,7 @@ inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float*
         p.pro_act = c->head_act; p.pro_slope = c->slope; p.pro_scale = hscale;
         p.W = weff + d.w_off; p.bias = weff + d.bias_off;
         p.Y = act + A.head1; p.ldy = 64; p.Cout = 64; p.B = B; p.T = T;
-        CRK_TRY(launch_conv(p, 2, s));
+        CRK_TRY(conv_dispatch(p, 2, weff + d.tc_off, d.tc_kpad, d.tc_n, s));
     }
     {
         const crk_conv_desc& d = L.tab.d[L.last2];
@@ -296,7 +304,7 @@ inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float*
         p.pro_act = c->head_act; p.pro_slope = c->slope;
         p.W = weff + d.w_off; p.bias = weff + d.bias_off;
         p.Y = y; p.ldy = ldy; p.Cout = c->out_ch; p.B = B; p.T = T;
-        CRK_TRY(launch_conv(p, cpt_for(c->out_ch), s));
+        CRK_TRY(conv_dispatch(p, cpt_for(c->out_ch), weff + d.tc_off, d.tc_kpad, d.tc_n, s));
     }
     return CRK_OK;
 }
@@ -332,7 +340,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
         p.X = dy; p.ldx = lddy; p.Cin = c->out_ch; p.CinPad = d.wt_rows;
         p.W = weff + d.wt_off; p.Y = ws + W.dhead1; p.ldy = 64; p.Cout = 64; p.B = B; p.T = T;
         p.dact_src = head1; p.lddact = 64; p.dact_mode = c->head_act; p.dact_slope = c->slope;
-        CRK_TRY(launch_conv(p, 2, s));
+        CRK_TRY(conv_dispatch(p, 2, weff + d.tct_off, d.tct_kpad, d.tct_n, s));
     }
     {
         const crk_conv_desc& d = L.tab.d[L.last1];
@@ -346,7 +354,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
         p.W = weff + d.wt_off; p.Y = ws + W.ds; p.ldy = 64; p.Cout = 64; p.B = B; p.T = T;
         p.dact_src = skips; p.lddact = 64; p.dact_mode = c->head_act; p.dact_slope = c->slope;
         p.out_scale = hscale;
-        CRK_TRY(launch_conv(p, 2, s));
+        CRK_TRY(conv_dispatch(p, 2, weff + d.tct_off, d.tct_kpad, d.tct_n, s));
     }
     // ---- residual blocks, last to first
     float* dh_cur = nullptr;              // grad wrt output of layer l (null for the last layer)
@@ -393,7 +401,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
                 p.X = ws + W.dg; p.ldx = 128; p.Cin = 128; p.CinPad = 128;
                 p.W = weff + d.wt_off; p.Y = dc; p.ldy = lddc; p.Cout = c->aux_ch; p.B = B; p.T = T;
                 p.accumulate = (l != c->layers - 1);
-                CRK_TRY(launch_conv(p, cpt_for(c->aux_ch), s));
+                CRK_TRY(conv_dispatch(p, cpt_for(c->aux_ch), weff + d.tct_off, d.tct_kpad, d.tct_n, s));
             }
         }
         {   // dgrad: dh_{l-1} = convT(dg) [* dropmul] + sqrt(.5)*dh_l ; (l==0: * first_act'(h0))
@@ -408,7 +416,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
             if (l == 0 && c->first_act != CRK_ACT_NONE) {
                 p.dact_src = h; p.lddact = 64; p.dact_mode = c->first_act; p.dact_slope = c->slope;
             }
-            CRK_TRY(launch_conv(p, 2, s));
+            CRK_TRY(conv_dispatch(p, 2, weff + d.tct_off, d.tct_kpad, d.tct_n, s));
             dh_cur = dst;
             flip ^= 1;
         }
@@ -425,7 +433,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
             ConvParams p = conv_params_default();
             p.X = dh_cur; p.ldx = 64; p.Cin = 64; p.CinPad = 64;
             p.W = weff + d.wt_off; p.Y = dx; p.ldy = lddx; p.Cout = c->in_ch; p.B = B; p.T = T;
-            CRK_TRY(launch_conv(p, cpt_for(c->in_ch), s));
+            CRK_TRY(conv_dispatch(p, cpt_for(c->in_ch), weff + d.tct_off, d.tct_kpad, d.tct_n, s));
         }
     }
     CRK_TRY(launch_weightnorm_bwd(L.tab, theta, gweff, gtheta, s));
@@ -513,7 +521,7 @@ inline int convstack_fwd(const crk_convstack_cfg* c, const float* weff, const fl
         if (last) { p.Y = y; p.ldy = ldy; }
         else { p.Y = act + off; p.ldy = L.cout[i]; p.epi_act = CRK_ACT_LRELU; p.epi_slope = c->slope; }
         p.Cout = L.cout[i];
-        CRK_TRY(launch_conv(p, cpt_for(L.cout[i]), s));
+        CRK_TRY(conv_dispatch(p, cpt_for(L.cout[i]), weff + d.tc_off, d.tc_kpad, d.tc_n, s));
         in = p.Y; ldin = p.ldy;
         if (!last) off += F * L.cout[i];
     }
@@ -559,7 +567,7 @@ inline int convstack_bwd(const crk_convstack_cfg* c, const float* theta, const f
             } else {
                 p.Y = dx; p.ldy = lddx; p.out_scale = dx_scale;
             }
-            CRK_TRY(launch_conv(p, cpt_for(L.cin[i]), s));
+            CRK_TRY(conv_dispatch(p, cpt_for(L.cin[i]), weff + d.tct_off, d.tct_kpad, d.tct_n, s));
             dcur = p.Y; lddcur = p.ldy;
             flip ^= 1;
         }

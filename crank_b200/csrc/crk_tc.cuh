@@ -17,6 +17,11 @@
 #include <stdint.h>
 
 namespace crk {
+// optional per-CTA phase timestamps (clock64) for performance debugging: crk_debug_timestamps(ptr)
+__device__ long long* g_crk_dbg = nullptr;
+__device__ __forceinline__ void dbg_stamp(int slot) {
+    if (g_crk_dbg && threadIdx.x == 64) g_crk_dbg[(size_t)blockIdx.x * 8 + slot] = clock64();
+}
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -48,6 +53,18 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t it = 0; it < (1u << 24); ++it)
         if (mbar_try_wait(bar, parity)) return true;
     return false;
+}
+// one arrival + expected transaction bytes (the bulk copies below complete the transaction count)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (one thread issues; the copy
+// engine streams the bytes: no register staging, no per-thread load latency).  16 B aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {

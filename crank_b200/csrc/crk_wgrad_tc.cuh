@@ -1,0 +1,252 @@
+// crank-b200: convolution weight gradients on tcgen05 (K-major TF32 / 3xTF32, reduction over frames).
+//
+//   dW_j[ci][co] = sum_frames X[f + j*dil - padl][ci] * G[f][co]
+// as  D_j^T[co (M=128)][ci (N)] = G^T . X_j  with the frame index as the UMMA K dimension.  Both
+// operands are staged TRANSPOSED into chunk-major tiles ([4-frame chunk][channel row][4 frames]) so
+// that they are K-major (MN-major tf32 operands are not usable with the no-swizzle layout -- measured,
+// tests/test_gpu_tc.py).  A tap shift is a shift along K, which a descriptor can only express in
+// multiples of 4 frames, so X^T is re-staged per tap (through a 2-slot ring, overlapped with the
+// previous tap's MMAs) while G^T is staged once per 64-frame tile.  All k taps accumulate in TMEM
+// (k x N columns) across every tile of the CTA's frame chunk; one epilogue per CTA writes the
+// per-chunk partial in the packed [tap][ci][co] layout k_reduce expects.
+#pragma once
+#include "crk_common.cuh"
+#include "crk_conv.cuh"
+#include "crk_resblock_tc.cuh"
+#include "crk_tc.cuh"
+
+namespace crk {
+
+#define CRK_WG_TF 64   // frames per tile (UMMA K = 64 per tile and tap)
+
+struct WgradTcParams {
+    WgradParams p;     // same contract as the fp32 kernel (p.part = [nchunk][k][Rows][TN])
+    int TN;            // packed columns of G / dW (32*cpt)
+    int Npad;          // UMMA N = round_up(Cin, 16)
+};
+
+// stage src[frame t0+shift .. +64)[0..ncols) transposed: elem(frame f, channel c) -> (f>>2)*cs + c*4 + (f&3).
+// Consecutive lanes take consecutive frames (conflict-free scatter); loads are batched 4 per thread
+// before use so that one L2 round trip covers the batch.
+template <bool SPLIT>
+__device__ __forceinline__ void wg_stage_T(float* hi, float* lo, int cs_floats, int nrows_pad,
+                                           const float* __restrict__ src, int ld, int ncols, int b, int T, int t0,
+                                           int shift, int pro_act, float pro_slope, float pro_scale,
+                                           const float* __restrict__ mul, int ldmul) {
+    const int c4n = nrows_pad >> 2;
+    const int total = CRK_WG_TF * c4n;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                     (mul == nullptr || (((ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mul) & 15) == 0)));
+    constexpr int U = 4;
+    for (int base0 = threadIdx.x; base0 < total; base0 += blockDim.x * U) {
+        float4 v[U], m[U];
+        int off[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = base0 + u * blockDim.x;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+            off[u] = -1;
+            if (idx < total) {
+                const int c4 = idx >> 6, f = idx & 63;
+                const int c = c4 * 4;
+                off[u] = (f >> 2) * cs_floats + c * 4 + (f & 3);
+                const int tg = t0 + f;
+                const int tt = tg + shift;
+                if (tg < T && tt >= 0 && tt < T && c < ncols) {
+                    const size_t row = (size_t)b * T + tt;
+                    if (vec && c + 3 < ncols) {
+                        v[u] = __ldg(reinterpret_cast<const float4*>(src + row * ld + c));
+                        if (mul) m[u] = __ldg(reinterpret_cast<const float4*>(mul + row * ldmul + c));
+                    } else {
+                        float t4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < ncols) {
+                                t4[e] = __ldg(src + row * ld + c + e);
+                                if (mul) m4[e] = __ldg(mul + row * ldmul + c + e);
+                            }
+                        v[u] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                        m[u] = make_float4(m4[0], m4[1], m4[2], m4[3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (off[u] < 0) continue;
+            const float x[4] = {apply_act(v[u].x * pro_scale, pro_act, pro_slope) * m[u].x,
+                                apply_act(v[u].y * pro_scale, pro_act, pro_slope) * m[u].y,
+                                apply_act(v[u].z * pro_scale, pro_act, pro_slope) * m[u].z,
+                                apply_act(v[u].w * pro_scale, pro_act, pro_slope) * m[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (SPLIT) {
+                    float h, l;
+                    tc::split_tf32(x[e], h, l);
+                    hi[off[u] + e * 4] = h;
+                    lo[off[u] + e * 4] = l;
+                } else {
+                    hi[off[u] + e * 4] = x[e];
+                }
+            }
+        }
+    }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams q) {
+    const WgradParams& p = q.p;
+    extern __shared__ float4 crk_smem4[];
+    float* smem = reinterpret_cast<float*>(crk_smem4);
+    __shared__ uint64_t bar_slot[2];
+    __shared__ uint64_t bar_tile;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int timeout_s;
+
+    constexpr int KCH = CRK_WG_TF / 4;                     // 16 frame chunks per tile
+    constexpr int CSG = 129 * 4;                           // G^T: 128 rows -> 129
+    const int csx = tc::chunk_rows(q.Npad) * 4;
+    float* Gh = smem;
+    float* Gl = Gh + KCH * CSG;
+    float* ring = Gl + (SPLIT ? KCH * CSG : 0);
+    const int xhalf = KCH * csx;
+    float* slot_hi[2] = {ring, ring + (SPLIT ? 2 : 1) * xhalf};
+    float* slot_lo[2] = {ring + xhalf, ring + 3 * xhalf};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int tiles_per_utt = (p.T + CRK_WG_TF - 1) / CRK_WG_TF;
+    const int ntiles = p.B * tiles_per_utt;
+    const int tile_beg = blockIdx.x * p.tiles_per_chunk;
+    const int tile_end = min(ntiles, tile_beg + p.tiles_per_chunk);
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bar_slot[0], 1); tc::mbar_init(&bar_slot[1], 1); tc::mbar_init(&bar_tile, 1);
+        tc::fence_mbar_init();
+        timeout_s = 0;
+    }
+    if (warp == 1) tc::tmem_alloc<512>(&tmem_base_s);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
+    const uint32_t gh_s = tc::smem_u32(Gh), gl_s = tc::smem_u32(Gl);
+    bool ok = true;
+    int step = 0;            // global (tile, tap) step counter -> ring slot + mbarrier phase
+    int ntile_done = 0;
+
+    auto stage_x = [&](int tile, int j, int slot) {
+        const int b = tile / tiles_per_utt;
+        const int t0 = (tile - b * tiles_per_utt) * CRK_WG_TF;
+        wg_stage_T<SPLIT>(slot_hi[slot], slot_lo[slot], csx, q.Npad, p.X, p.ldx, p.Cin, b, p.T, t0,
+                          j * p.dil - p.padl, p.pro_act, p.pro_slope, p.pro_scale, p.xmul, p.ldxmul);
+    };
+
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+        const int b = tile / tiles_per_utt;
+        const int t0 = (tile - b * tiles_per_utt) * CRK_WG_TF;
+        // G^T is read by every MMA of the previous tile: wait for them before overwriting it
+        if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
+        wg_stage_T<SPLIT>(Gh, Gl, CSG, 128, p.G, p.ldg, p.N, b, p.T, t0, 0, CRK_ACT_NONE, 0.f, 1.f, nullptr, 0);
+        // first tap's X^T (its slot was released by the tile-level wait above, or is fresh)
+        stage_x(tile, 0, step & 1);
+        tc::fence_proxy_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        for (int j = 0; j < p.k; ++j, ++step) {
+            if (threadIdx.x == 0) {
+                uint32_t acc = ntile_done > 0 ? 1u : 0u;
+                // A = G^T (M = 128 rows = co), B = X_j^T (N rows = ci), K = 64 frames
+                tc_issue_kmajor<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi[step & 1]),
+                                       tc::smem_u32(slot_lo[step & 1]), csx * 4, CRK_WG_TF, idesc, acc);
+                tc::umma_commit(&bar_slot[step & 1]);
+                if (j == p.k - 1) tc::umma_commit(&bar_tile);
+            }
+            if (j + 1 < p.k) {
+                const int nstep = step + 1;
+                // slot (nstep&1) was last used by step nstep-2 (this tile or the previous one)
+                if (nstep >= 2) ok &= tc::mbar_wait(&bar_slot[nstep & 1], ((nstep - 2) >> 1) & 1);
+                stage_x(tile, j + 1, nstep & 1);
+                tc::fence_proxy_async_smem();
+                __syncthreads();
+            }
+        }
+        ++ntile_done;
+    }
+    if (ntile_done > 0) ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1);
+    tc::tc_fence_after();
+    if (!ok) timeout_s = 1;
+    __syncthreads();
+
+    // ---- epilogue: D_j^T[co][ci] -> part[chunk][j][ci][co] ----
+    const int co = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* out = p.part + (size_t)blockIdx.x * p.k * p.Rows * q.TN;
+    const int nblk = (q.Npad + 31) >> 5;
+    const float poison = __int_as_float(0x7fc00000);
+    for (int j = 0; j < p.k; ++j)
+        for (int blk = warp >> 2; blk < nblk; blk += 2) {
+            float v[32];
+            if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
+            if (co >= q.TN) continue;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int ci = blk * 32 + i;
+                if (ci < p.Rows)
+                    out[((size_t)j * p.Rows + ci) * q.TN + co] = timeout_s ? poison : (ntile_done > 0 ? v[i] : 0.f);
+            }
+        }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
+inline size_t wgrad_tc_smem(int Npad, bool split) {
+    const size_t g = (size_t)16 * 129 * 4, x = (size_t)16 * tc::chunk_rows(Npad) * 4;
+    return ((split ? 2 : 1) * g + (split ? 4 : 2) * x) * sizeof(float);
+}
+inline bool wgrad_tc_ok(const WgradParams& p, int TN, int Npad, bool split) {
+    return TN <= 128 && Npad >= 16 && Npad <= 128 && p.k * Npad <= 512 && p.Rows <= Npad &&
+           wgrad_tc_smem(Npad, split) <= 220 * 1024;
+}
+
+struct WgradTcWork { int nchunk, tiles_per_chunk; };
+inline WgradTcWork wgrad_tc_work(int B, int T) {
+    const int ntiles = B * cdiv(T, CRK_WG_TF);
+    int nchunk = ntiles < 148 ? ntiles : 148;
+    WgradTcWork w;
+    w.tiles_per_chunk = cdiv(ntiles, nchunk);
+    w.nchunk = cdiv(ntiles, w.tiles_per_chunk);
+    return w;
+}
+
+template <bool SPLIT>
+inline cudaError_t launch_wgrad_tc_t(const WgradTcParams& q, int nchunk, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    TimedLaunch tl(CRK_K_WGRAD, s);
+    k_wgrad_tc<SPLIT><<<nchunk, 256, wgrad_tc_smem(q.Npad, SPLIT), s>>>(q);
+    return launch_check();
+}
+
+inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err) {
+    const int mode = precision_mode();
+    if (mode == CRK_PREC_FP32) return false;
+    const bool split = mode == CRK_PREC_TF32X3;
+    const int Npad = round_up(p.Cin, 16);
+    if (!wgrad_tc_ok(p, TN, Npad, split)) return false;
+    const WgradTcWork w = wgrad_tc_work(p.B, p.T);
+    WgradTcParams q;
+    q.p = p; q.p.part = part; q.p.tiles_per_chunk = w.tiles_per_chunk; q.TN = TN; q.Npad = Npad;
+    *nchunk = w.nchunk;
+    *err = split ? launch_wgrad_tc_t<true>(q, w.nchunk, s) : launch_wgrad_tc_t<false>(q, w.nchunk, s);
+    return true;
+}
+
+}  // namespace crk

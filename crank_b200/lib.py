@@ -37,7 +37,8 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("g_off", i32), ("v_off", i32), ("b_off", i32), ("cout", i32), ("cin", i32), ("k", i32),
         ("w_off", i32), ("bias_off", i32), ("cin_pad", i32), ("ldw", i32), ("perm", i32),
-        ("wt_off", i32), ("wt_rows", i32), ("ldwt", i32), ("tc_off", i32), ("tc_kpad", i32),
+        ("wt_off", i32), ("wt_rows", i32), ("ldwt", i32), ("tc_off", i32), ("tc_kpad", i32), ("tc_n", i32),
+        ("tct_off", i32), ("tct_kpad", i32), ("tct_n", i32),
     ]
 
 
@@ -53,6 +54,7 @@ SIGNATURES = {
     "crk_version": (i32, []),
     "crk_set_precision": (i32, [i32]),
     "crk_get_precision": (i32, []),
+    "crk_debug_timestamps": (i32, [vp]),
     "crk_launch_count": (C.c_ulonglong, []),
     "crk_timing_enable": (i32, [i32]),
     "crk_timing_read": (i32, [C.POINTER(i32), C.POINTER(f32)]),
@@ -89,6 +91,7 @@ SIGNATURES = {
     "crk_logmel_fwd": (i32, [vp, i32, i64, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
 }
 
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
 _lib = None
 LAUNCHES = 0  # number of C-ABI compute calls issued (each launches >= 1 of our kernels)
 
@@ -108,6 +111,11 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        # default arithmetic of the dense contractions: the 3xTF32 tensor-core parity mode
+        mode = os.environ.get("CRANK_B200_PRECISION", "tf32x3")
+        if mode not in PRECISIONS:
+            raise RuntimeError(f"CRANK_B200_PRECISION={mode!r}: expected one of {sorted(PRECISIONS)}")
+        handle.crk_set_precision(PRECISIONS[mode])
     return _lib
 
 
@@ -166,9 +174,6 @@ def describe_convstack(cfg):
     check(lib().crk_convstack_describe(C.byref(cfg), descs, C.byref(n), C.byref(th), C.byref(we)),
           "crk_convstack_describe")
     return [descs[i] for i in range(n.value)], th.value, we.value
-
-
-PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}
 
 
 def set_precision(mode):

@@ -44,6 +44,9 @@ int crk_get_precision(void);
  * timing of one kernel family (ids: 1 resblock_fwd, 2 wgrad, 3 conv, 4 resblock_bwd_gate, 5 vq_argmin;
  * 0 disables).  crk_timing_read synchronises the device and returns (#launches, total ms) since enable. */
 unsigned long long crk_launch_count(void);
+/* performance debugging: device buffer of gridDim*8 int64 that tensor-core kernels fill with clock64()
+ * phase stamps (NULL disables) */
+int crk_debug_timestamps(long long* device_buffer);
 int crk_timing_enable(int kernel_id);
 int crk_timing_read(int* count, float* total_ms);
 
@@ -78,8 +81,11 @@ typedef struct {
     int w_off, bias_off;         /* offsets into the packed effective-weight buffer ("weff") */
     int cin_pad, ldw, perm;      /* fwd packing  W[j][cin_pad][ldw], column permutation id */
     int wt_off, wt_rows, ldwt;   /* transposed, tap-flipped copy for dgrad; wt_off < 0: none */
-    int tc_off, tc_kpad;         /* tensor-core operand blobs (chunk-major, tf32 hi|lo split) per tap;
-                                    tc_off < 0: none.  tc_kpad = K rounded up to 8 */
+    /* tensor-core B-operand blobs (chunk-major, tf32 hi|lo split), one per tap:
+     *   forward: rows n = packed output column (tc_n rows, UMMA N), K = input channel (tc_kpad)
+     *   dgrad  : rows n = input channel (tct_n), K = packed output column (tct_kpad), taps flipped */
+    int tc_off, tc_kpad, tc_n;
+    int tct_off, tct_kpad, tct_n;
 } crk_conv_desc;
 
 #define CRK_MAX_CONVS 64

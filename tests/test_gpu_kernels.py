@@ -12,6 +12,16 @@ from tests.util import assert_close, compare_conv_grads, rel_err
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _fp32_cuda_core_path():
+    """this file pins the fp32 CUDA-core kernels; tests/test_gpu_tc.py repeats it on the tensor cores"""
+    from crank_b200 import lib as L
+
+    L.set_precision("fp32")
+    yield
+    L.set_precision("tf32x3")
+
 TOL = 1e-4
 
 
