@@ -51,8 +51,10 @@ int crk_set_precision(int mode) {
     return CRK_OK;
 }
 int crk_get_precision(void) { return precision_mode(); }
-int crk_debug_timestamps(long long* device_buffer) {
+int crk_debug_timestamps(long long* device_buffer, int kernel_id, int launch_index) {
     API_TRY(cudaMemcpyToSymbol(g_crk_dbg, &device_buffer, sizeof(device_buffer)));
+    DbgSel& d = dbg_sel();
+    d.kind = device_buffer ? kernel_id : 0; d.target = launch_index; d.count = 0;
     return CRK_OK;
 }
 unsigned long long crk_launch_count(void) { return instr().launches; }

@@ -177,7 +177,8 @@ struct WgradParams {
     int pro_act; float pro_slope; float pro_scale;
     const float* xmul; int ldxmul;
     const float* G; int ldg; int N;                // N real columns of G (<= TN)
-    float* part;                                   // [nchunk][k][Rows][TN]
+    float* part;                                   // [nchunk][part_stride]: per chunk [k][Rows][TN] (+ bias partial)
+    long long part_stride;
     int B, T, k, dil, padl;
     int tiles_per_chunk;
 };
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(CRK_THREADS) k_wgrad(const WgradParams p) {
         __syncthreads();
         tile_mac_colA<CPT>(acc, xs + ty * 8, 64, gs + tx * CPT, TN, CRK_TM);
     }
-    float* out = p.part + ((size_t)blockIdx.x * p.k + j) * p.Rows * TN;
+    float* out = p.part + (size_t)blockIdx.x * p.part_stride + (size_t)j * p.Rows * TN;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = rb + ty * 8 + i;
@@ -276,11 +277,12 @@ __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ part, 
     }
 }
 
-// per-chunk column sums: part[chunk*2 + g][n],  block = 256 threads = 2 row groups x 128 columns;
-// 4 independent accumulators per thread keep 4 loads in flight
+// per-chunk column sums (bias gradients): part[chunk * stride + n], block = 2 row groups x 128 columns;
+// 4 independent accumulators per thread keep 4 loads in flight; fixed summation order.
 __global__ void __launch_bounds__(CRK_THREADS) k_colsum(const float* __restrict__ G, int ldg, int N,
                                                          long long F, int rows_per_chunk,
-                                                         float* __restrict__ part, int TN) {
+                                                         float* __restrict__ part, int TN, long long stride) {
+    __shared__ float red[128];
     const int n = threadIdx.x & 127, g = threadIdx.x >> 7;
     const long long beg = (long long)blockIdx.x * rows_per_chunk;
     const long long end = min(F, beg + rows_per_chunk);
@@ -295,7 +297,10 @@ __global__ void __launch_bounds__(CRK_THREADS) k_colsum(const float* __restrict_
         }
         for (; r < end; r += 2) s0 += __ldg(G + r * ldg + n);
     }
-    if (n < TN) part[((size_t)blockIdx.x * 2 + g) * TN + n] = (s0 + s1) + (s2 + s3);
+    const float s = (s0 + s1) + (s2 + s3);
+    if (g == 1) red[n] = s;
+    __syncthreads();
+    if (g == 0 && n < TN) part[(size_t)blockIdx.x * stride + n] = s + red[n];
 }
 
 // Work-partition policy of wgrad: number of per-chunk partials so that the (chunk, tap, rowblock)
@@ -314,23 +319,15 @@ inline WgradWork wgrad_work(int B, int T, int k, int rows) {
     w.nchunk = cdiv(ntiles, w.tiles_per_chunk);
     return w;
 }
-inline int colsum_chunks(long long F) {
-    long long n = cdivl(F, 64);
-    if (n > 148 * 4) n = 148 * 4;
-    if (n < 1) n = 1;
-    return (int)n;
-}
-
 // Scratch floats conv_wgrad() needs for a conv of k taps, `rows` packed input rows, tn packed columns.
 inline size_t wgrad_part_floats(int B, int T, int k, int rows, int tn) {
     WgradWork w = wgrad_work(B, T, k, rows);
-    size_t a = (size_t)w.nchunk * k * rows * tn;
-    size_t b = (size_t)colsum_chunks((long long)B * T) * 2 * tn;
+    // per chunk: [k][rows][tn] weight-gradient partial followed by a [tn] bias-gradient partial
+    size_t a = (size_t)w.nchunk * ((size_t)k * rows * tn + tn);
     // tensor-core wgrad policy (crk_wgrad_tc.cuh): up to 148 chunks of 64-frame tiles
     const int ntiles64 = B * cdiv(T, 64);
-    size_t c = (size_t)(ntiles64 < 148 ? ntiles64 : 148) * k * rows * tn;
-    a = a > c ? a : c;
-    return a > b ? a : b;
+    size_t c = (size_t)(ntiles64 < 148 ? ntiles64 : 148) * ((size_t)k * rows * tn + tn);
+    return a > c ? a : c;
 }
 
 template <int CPT>
@@ -351,10 +348,16 @@ inline cudaError_t launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t 
 bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err);
 
 // dW (and db when non-null) of one convolution.  cpt gives the packing of the G columns (TN=32*cpt).
+// dW and db must be adjacent (db == dW + k*Rows*TN, the packed weff layout) so that ONE deterministic
+// reduction launch sums both partial sets.
 inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, float* part,
                               cudaStream_t s) {
     const int TN = 32 * cpt;
+    const int nW = p.k * p.Rows * TN;
+    const bool fused_bias = db != nullptr && db == dW + nW;
+    const long long stride = nW + (fused_bias ? TN : 0);     // floats per chunk in `part`
     p.part = part;
+    p.part_stride = stride;
     cudaError_t e = cudaSuccess;
     int nchunk = 0;
     if (!wgrad_tc_try(p, TN, part, s, &nchunk, &e)) {
@@ -370,18 +373,26 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
         }
     }
     if (e != cudaSuccess) return e;
-    const int n = p.k * p.Rows * TN;
+    const long long F = (long long)p.B * p.T;
+    if (fused_bias) {
+        const int rows_per_chunk = (int)cdivl(F, nchunk);     // chunk c may be empty: it then writes zeros
+        k_colsum<<<nchunk, CRK_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part + nW, TN, stride);
+        e = launch_check();
+        if (e != cudaSuccess) return e;
+    }
+    const int n = (int)stride;
     k_reduce<<<cdiv(n, 128), 256, 0, s>>>(part, nchunk, n, dW, 0);
     e = launch_check();
     if (e != cudaSuccess) return e;
-    if (db) {
-        const long long F = (long long)p.B * p.T;
-        const int rows_per_chunk = (int)cdivl(F, colsum_chunks(F));
-        const int nch = (int)cdivl(F, rows_per_chunk);
-        k_colsum<<<nch, CRK_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part, TN);
+    if (db && !fused_bias) {
+        int nch = (int)cdivl(F, 256);
+        if (nch > nchunk) nch = nchunk;
+        if (nch < 1) nch = 1;
+        const int rows_per_chunk = (int)cdivl(F, nch);
+        k_colsum<<<nch, CRK_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part, TN, TN);
         e = launch_check();
         if (e != cudaSuccess) return e;
-        k_reduce<<<cdiv(TN, 128), 256, 0, s>>>(part, nch * 2, TN, db, 0);
+        k_reduce<<<cdiv(TN, 128), 256, 0, s>>>(part, nch, TN, db, 0);
         e = launch_check();
     }
     return e;

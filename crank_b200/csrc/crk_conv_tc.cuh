@@ -19,16 +19,18 @@ struct ConvTcParams {
     ConvParams p;
     const float* Wtc;     // per tap: hi [Kpad/4][chunk_rows(Npad)][4] | lo [same]
     int Kpad, Npad;       // K rounded up to 8, UMMA N (multiple of 16, <= 128)
+    int dbg;
 };
 
-template <bool SPLIT>
+template <bool SPLIT, int U>
 __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_floats, const ConvParams& p, int Kpad,
                                                  int b, int tstart, int rows) {
     const int c4n = Kpad >> 2;
     const int total = rows * c4n;
     const bool vec = ((p.ldx & 3) == 0) && ((p.Cin & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
                      (p.xmul == nullptr || (((p.ldxmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.xmul) & 15) == 0)));
-    constexpr int U = 4;
+    // U independent float4 loads per thread per round: with one CTA (8 warps) per SM every global round
+    // trip costs ~2-3K cycles (measured), so the whole tile should be in flight at once when it fits
     for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
         float4 v[U], m[U];
         int off[U];
@@ -87,7 +89,7 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
 }
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(256, 1) k_conv_tc(const ConvTcParams q) {
+__global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcParams q) {
     const ConvParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
@@ -137,18 +139,27 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(const ConvTcParams q) {
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     bool ok = true;
+    dbg_stamp(q.dbg, 0);
     if (threadIdx.x == 0)
         for (int st = 0; st < 2 && st < nsteps; ++st) produce(st);
-    tc_stage_act_pro<SPLIT>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
+    // (deeper batches were measured: no gain in the 3xTF32 mode, and the extra registers cost the plain
+    //  TF32 variant its second resident CTA per SM, which matters far more)
+    tc_stage_act_pro<SPLIT, 4>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
     tc::fence_proxy_async_smem();
     __syncthreads();
+    dbg_stamp(q.dbg, 1);
 
-    if (threadIdx.x == 0) {
-        for (int st = 2; st < nsteps; ++st) {
-            ok &= tc::mbar_wait(&bar_free[st & 1], ((st - 2) >> 1) & 1);
-            produce(st);
-        }
-    } else if (threadIdx.x == 32) {
+    // one elected lane per role; the other 31 lanes of that warp park at __syncwarp (no spinning next to
+    // the working lane)
+    if (warp == 0) {
+        if (lane == 0)
+            for (int st = 2; st < nsteps; ++st) {
+                ok &= tc::mbar_wait(&bar_free[st & 1], ((st - 2) >> 1) & 1);
+                produce(st);
+            }
+        __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
         const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
         const uint32_t xh_s = tc::smem_u32(Xh), xl_s = tc::smem_u32(Xl);
         uint32_t acc = 0;
@@ -164,10 +175,13 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(const ConvTcParams q) {
             tc::umma_commit(&bar_free[st & 1]);
         }
         tc::umma_commit(&bar_acc);
+      }
+      __syncwarp();
     }
     ok &= tc::mbar_wait(&bar_acc, 0);
     tc::tc_fence_after();
     if (!ok) timeout_s = 1;
+    dbg_stamp(q.dbg, 2);
 
     // ---- epilogue (same option order as k_conv) ----
     // TMEM -> registers is thread-per-row; the accumulators are transposed through a padded smem tile
@@ -187,6 +201,7 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(const ConvTcParams q) {
         }
     }
     __syncthreads();
+    dbg_stamp(q.dbg, 3);
     {
         const int nlive = min(CRK_TC_TM, p.T - t0);
         const size_t row0 = (size_t)b * p.T + t0;
@@ -228,6 +243,7 @@ __global__ void __launch_bounds__(256, 1) k_conv_tc(const ConvTcParams q) {
     }
     tc::tc_fence_before();
     __syncthreads();
+    dbg_stamp(q.dbg, 4);
     if (timeout_s && threadIdx.x == 0) p.Y[((size_t)b * p.T + t0) * p.ldy] = __int_as_float(0x7fc00000);
     if (warp == 1) tc::tmem_dealloc<128>(tmem);
 }
@@ -256,7 +272,9 @@ inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
     }
     const int tiles = q.p.B * cdiv(q.p.T, CRK_TC_TM);
     TimedLaunch tl(CRK_K_CONV, s);
-    k_conv_tc<SPLIT><<<tiles, 256, conv_tc_smem(q, SPLIT), s>>>(q);
+    ConvTcParams qq = q;
+    qq.dbg = dbg_take(CRK_K_CONV);
+    k_conv_tc<SPLIT><<<tiles, 256, conv_tc_smem(q, SPLIT), s>>>(qq);
     return launch_check();
 }
 
@@ -265,7 +283,7 @@ inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc,
     const int mode = precision_mode();
     if (mode != CRK_PREC_FP32) {
         ConvTcParams q;
-        q.p = p; q.Wtc = wtc; q.Kpad = kpad; q.Npad = npad;
+        q.p = p; q.Wtc = wtc; q.Kpad = kpad; q.Npad = npad; q.dbg = 0;
         const bool split = mode == CRK_PREC_TF32X3;
         if (conv_tc_ok(q, split)) return split ? launch_conv_tc_t<true>(q, s) : launch_conv_tc_t<false>(q, s);
     }

@@ -28,6 +28,7 @@ struct ResFwdTcParams {
     const float* WaTc;       // aux blob: hi [KaPad/4][129][4] | lo   (KaPad = round_up(Ca, 8))
     const float* WosTc;      // blob hi [16][129][4] | lo
     int KaPad;
+    int dbg;
 };
 
 __host__ __device__ constexpr int tc_blob_half(int kdim, int nrows) { return (kdim / 4) * tc::chunk_rows(nrows) * 4; }
@@ -122,7 +123,7 @@ __device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.f, 
 __device__ __forceinline__ float gate_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(256, 1) k_resblock_fwd_tc(const ResFwdTcParams q) {
+__global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const ResFwdTcParams q) {
     const ResFwdParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
@@ -174,26 +175,30 @@ __global__ void __launch_bounds__(256, 1) k_resblock_fwd_tc(const ResFwdTcParams
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     bool ok = true;
-    dbg_stamp(0);
+    dbg_stamp(q.dbg, 0);
 
     // ---- producer: first two blobs in flight while everybody stages the activation tile ----
     if (threadIdx.x == 0) {
         for (int bi = 0; bi < 2 && bi < nblobs; ++bi)
             tc_bulk_blob<SPLIT>(slot_hi[bi & 1], slot_lo[bi & 1], blob_src(bi), blob_half(bi), blob_half(bi), &bar_full[bi & 1]);
     }
-    tc_stage_act<SPLIT, 9>(Xh, Xl, csx, p.Hin, 64, 64, 64, b, p.T, t0 - p.padl, rowsX, p.dropmul, 64);
+    tc_stage_act<SPLIT, SPLIT ? 9 : 5>(Xh, Xl, csx, p.Hin, 64, 64, 64, b, p.T, t0 - p.padl, rowsX, p.dropmul, 64);
     tc::fence_proxy_async_smem();
     __syncthreads();
-    dbg_stamp(1);
+    dbg_stamp(q.dbg, 1);
 
     const uint32_t idesc = tc::make_idesc_tf32(128, 128, 0, 0);
-    if (threadIdx.x == 0) {
+    // one elected lane per role; the other 31 lanes of that warp park at __syncwarp (no spinning)
+    if (warp == 0) {
         // ===== TMA producer: refill a ring slot as soon as the MMAs that read it have completed =====
-        for (int bi = 2; bi < nblobs; ++bi) {
-            ok &= tc::mbar_wait(&bar_free[bi & 1], ((bi - 2) >> 1) & 1);
-            tc_bulk_blob<SPLIT>(slot_hi[bi & 1], slot_lo[bi & 1], blob_src(bi), blob_half(bi), blob_half(bi), &bar_full[bi & 1]);
-        }
-    } else if (threadIdx.x == 32) {
+        if (lane == 0)
+            for (int bi = 2; bi < nblobs; ++bi) {
+                ok &= tc::mbar_wait(&bar_free[bi & 1], ((bi - 2) >> 1) & 1);
+                tc_bulk_blob<SPLIT>(slot_hi[bi & 1], slot_lo[bi & 1], blob_src(bi), blob_half(bi), blob_half(bi), &bar_full[bi & 1]);
+            }
+        __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
         // ===== MMA issuer: conv taps =====
         const uint32_t xh_s = tc::smem_u32(Xh), xl_s = tc::smem_u32(Xl);
         uint32_t acc = 0;
@@ -206,6 +211,8 @@ __global__ void __launch_bounds__(256, 1) k_resblock_fwd_tc(const ResFwdTcParams
         }
         tc::umma_commit(&bar_acc[0]);
         if (!has_aux) tc::umma_commit(&bar_acc[1]);
+      }
+      __syncwarp();
     }
     // ---- aux 1x1 (decoder 0): its tile reuses the X region -> all tap MMAs must have completed ----
     if (has_aux) {
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(256, 1) k_resblock_fwd_tc(const ResFwdTcParams
     }
     ok &= tc::mbar_wait(&bar_acc[1], 0);
     tc::tc_fence_after();
-    dbg_stamp(2);
+    dbg_stamp(q.dbg, 2);
 
     // ---- epilogue 1: gate ----
     // TMEM -> registers is thread-per-row; a thread-per-row GLOBAL access pattern costs 32 line
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(256, 1) k_resblock_fwd_tc(const ResFwdTcParams
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    dbg_stamp(3);
+    dbg_stamp(q.dbg, 3);
 
     // ---- GEMM2: [out | skip] (async) while every warp streams the saved gates out, row-coalesced ----
     if (threadIdx.x == 32) {
@@ -303,7 +310,7 @@ __global__ void __launch_bounds__(256, 1) k_resblock_fwd_tc(const ResFwdTcParams
     }
     ok &= tc::mbar_wait(&bar_acc[2], 0);
     tc::tc_fence_after();
-    dbg_stamp(4);
+    dbg_stamp(q.dbg, 4);
 
     // ---- epilogue 2: (acc2 + bias) -> padded smem tile -> coalesced residual / skip pass ----
     if (!ok) timeout_s = 1;
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(256, 1) k_resblock_fwd_tc(const ResFwdTcParams
     }
     tc::tc_fence_before();
     __syncthreads();
-    dbg_stamp(5);
+    dbg_stamp(q.dbg, 5);
     if (timeout_s && threadIdx.x == 0) p.Hout[((size_t)b * p.T + t0) * 64] = __int_as_float(0x7fc00000);  // poison: test must fail
     if (warp == 1) tc::tmem_dealloc<256>(tmem);
 }
@@ -373,7 +380,9 @@ inline cudaError_t launch_resblock_fwd_tc(const ResFwdTcParams& q, cudaStream_t 
     }
     const int tiles = q.p.B * cdiv(q.p.T, CRK_TC_TM);
     TimedLaunch tl(CRK_K_RESBLOCK_FWD, s);
-    k_resblock_fwd_tc<SPLIT><<<tiles, 256, resblock_fwd_tc_smem(q.p.k, q.p.dil), s>>>(q);
+    ResFwdTcParams qq = q;
+    qq.dbg = dbg_take(CRK_K_RESBLOCK_FWD);
+    k_resblock_fwd_tc<SPLIT><<<tiles, 256, resblock_fwd_tc_smem(q.p.k, q.p.dil), s>>>(qq);
     return launch_check();
 }
 

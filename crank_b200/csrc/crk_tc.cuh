@@ -19,8 +19,16 @@
 namespace crk {
 // optional per-CTA phase timestamps (clock64) for performance debugging: crk_debug_timestamps(ptr)
 __device__ long long* g_crk_dbg = nullptr;
-__device__ __forceinline__ void dbg_stamp(int slot) {
-    if (g_crk_dbg && threadIdx.x == 64) g_crk_dbg[(size_t)blockIdx.x * 8 + slot] = clock64();
+__device__ __forceinline__ void dbg_stamp(int enabled, int slot) {
+    if (enabled && g_crk_dbg && threadIdx.x == 64) g_crk_dbg[(size_t)blockIdx.x * 16 + slot] = clock64();
+}
+// host side: which launch of which kernel family records stamps
+struct DbgSel { int kind = 0; int target = 0; int count = 0; };
+inline DbgSel& dbg_sel() { static DbgSel d; return d; }
+inline int dbg_take(int kind) {
+    DbgSel& d = dbg_sel();
+    if (d.kind != kind) return 0;
+    return (d.count++ == d.target) ? 1 : 0;
 }
 namespace tc {
 

@@ -23,79 +23,87 @@ struct WgradTcParams {
     WgradParams p;     // same contract as the fp32 kernel (p.part = [nchunk][k][Rows][TN])
     int TN;            // packed columns of G / dW (32*cpt)
     int Npad;          // UMMA N = round_up(Cin, 16)
+    int dbg;
 };
 
-// stage src[frame t0+shift .. +64)[0..ncols) transposed: elem(frame f, channel c) -> (f>>2)*cs + c*4 + (f&3).
-// Consecutive lanes take consecutive frames (conflict-free scatter); loads are batched 4 per thread
-// before use so that one L2 round trip covers the batch.
-template <bool SPLIT>
-__device__ __forceinline__ void wg_stage_T(float* hi, float* lo, int cs_floats, int nrows_pad,
-                                           const float* __restrict__ src, int ld, int ncols, int b, int T, int t0,
-                                           int shift, int pro_act, float pro_slope, float pro_scale,
-                                           const float* __restrict__ mul, int ldmul) {
-    const int c4n = nrows_pad >> 2;
-    const int total = CRK_WG_TF * c4n;
+// Transposed staging of src[frame t0+shift .. +64)[0..ncols):  elem(frame f, channel c) -> (f>>2)*cs + c*4 + (f&3).
+// Split in two phases so that the global loads can be issued BEFORE waiting on the mbarrier that
+// guards the destination buffer (their latency overlaps the wait / the running MMAs):
+//   wg_load  : NB float4 per thread into registers (consecutive lanes = consecutive frames)
+//   wg_store : prologue, tf32 hi/lo split, conflict-free scalar scatter into the chunk-major tile
+template <int NB>
+struct WgRegs {
+    float4 v[NB];
+    float4 m[NB];
+};
+
+template <int NB>
+__device__ __forceinline__ void wg_load(WgRegs<NB>& R, int nrows_pad, const float* __restrict__ src, int ld, int ncols,
+                                        int b, int T, int t0, int shift, const float* __restrict__ mul, int ldmul) {
+    const int total = CRK_WG_TF * (nrows_pad >> 2);
     const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
                      (mul == nullptr || (((ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mul) & 15) == 0)));
-    constexpr int U = 4;
-    for (int base0 = threadIdx.x; base0 < total; base0 += blockDim.x * U) {
-        float4 v[U], m[U];
-        int off[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int idx = base0 + u * blockDim.x;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-            off[u] = -1;
-            if (idx < total) {
-                const int c4 = idx >> 6, f = idx & 63;
-                const int c = c4 * 4;
-                off[u] = (f >> 2) * cs_floats + c * 4 + (f & 3);
-                const int tg = t0 + f;
-                const int tt = tg + shift;
-                if (tg < T && tt >= 0 && tt < T && c < ncols) {
-                    const size_t row = (size_t)b * T + tt;
-                    if (vec && c + 3 < ncols) {
-                        v[u] = __ldg(reinterpret_cast<const float4*>(src + row * ld + c));
-                        if (mul) m[u] = __ldg(reinterpret_cast<const float4*>(mul + row * ldmul + c));
-                    } else {
-                        float t4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {1.f, 1.f, 1.f, 1.f};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (c + e < ncols) {
-                                t4[e] = __ldg(src + row * ld + c + e);
-                                if (mul) m4[e] = __ldg(mul + row * ldmul + c + e);
-                            }
-                        v[u] = make_float4(t4[0], t4[1], t4[2], t4[3]);
-                        m[u] = make_float4(m4[0], m4[1], m4[2], m4[3]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (off[u] < 0) continue;
-            const float x[4] = {apply_act(v[u].x * pro_scale, pro_act, pro_slope) * m[u].x,
-                                apply_act(v[u].y * pro_scale, pro_act, pro_slope) * m[u].y,
-                                apply_act(v[u].z * pro_scale, pro_act, pro_slope) * m[u].z,
-                                apply_act(v[u].w * pro_scale, pro_act, pro_slope) * m[u].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (SPLIT) {
-                    float h, l;
-                    tc::split_tf32(x[e], h, l);
-                    hi[off[u] + e * 4] = h;
-                    lo[off[u] + e * 4] = l;
+    for (int u = 0; u < NB; ++u) {
+        const int idx = threadIdx.x + u * 256;
+        R.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        R.m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (idx < total) {
+            const int c4 = idx >> 6, f = idx & 63;
+            const int c = c4 * 4;
+            const int tg = t0 + f;
+            const int tt = tg + shift;
+            if (tg < T && tt >= 0 && tt < T && c < ncols) {
+                const size_t row = (size_t)b * T + tt;
+                if (vec && c + 3 < ncols) {
+                    R.v[u] = __ldg(reinterpret_cast<const float4*>(src + row * ld + c));
+                    if (mul) R.m[u] = __ldg(reinterpret_cast<const float4*>(mul + row * ldmul + c));
                 } else {
-                    hi[off[u] + e * 4] = x[e];
+                    float t4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (c + e < ncols) {
+                            t4[e] = __ldg(src + row * ld + c + e);
+                            if (mul) m4[e] = __ldg(mul + row * ldmul + c + e);
+                        }
+                    R.v[u] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                    R.m[u] = make_float4(m4[0], m4[1], m4[2], m4[3]);
                 }
             }
         }
     }
 }
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams q) {
+template <bool SPLIT, int NB>
+__device__ __forceinline__ void wg_store(const WgRegs<NB>& R, float* hi, float* lo, int cs_floats, int nrows_pad,
+                                         int pro_act, float pro_slope, float pro_scale) {
+    const int total = CRK_WG_TF * (nrows_pad >> 2);
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        const int idx = threadIdx.x + u * 256;
+        if (idx >= total) continue;
+        const int c4 = idx >> 6, f = idx & 63;
+        const int off = (f >> 2) * cs_floats + c4 * 16 + (f & 3);
+        const float x[4] = {apply_act(R.v[u].x * pro_scale, pro_act, pro_slope) * R.m[u].x,
+                            apply_act(R.v[u].y * pro_scale, pro_act, pro_slope) * R.m[u].y,
+                            apply_act(R.v[u].z * pro_scale, pro_act, pro_slope) * R.m[u].z,
+                            apply_act(R.v[u].w * pro_scale, pro_act, pro_slope) * R.m[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (SPLIT) {
+                float h, l;
+                tc::split_tf32(x[e], h, l);
+                hi[off + e * 4] = h;
+                lo[off + e * 4] = l;
+            } else {
+                hi[off + e * 4] = x[e];
+            }
+        }
+    }
+}
+
+template <bool SPLIT, int NX>
+__global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(const WgradTcParams q) {
     const WgradParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
@@ -136,27 +144,43 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams q) {
     int step = 0;            // global (tile, tap) step counter -> ring slot + mbarrier phase
     int ntile_done = 0;
 
-    auto stage_x = [&](int tile, int j, int slot) {
-        const int b = tile / tiles_per_utt;
-        const int t0 = (tile - b * tiles_per_utt) * CRK_WG_TF;
-        wg_stage_T<SPLIT>(slot_hi[slot], slot_lo[slot], csx, q.Npad, p.X, p.ldx, p.Cin, b, p.T, t0,
-                          j * p.dil - p.padl, p.pro_act, p.pro_slope, p.pro_scale, p.xmul, p.ldxmul);
+    // G^T tile = 64 frames x 128 channels = 8 float4 per thread; X^T tile = NX float4 per thread (4 when
+    // Npad <= 64).  The X loads of tap j+1 are issued BEFORE the MMAs of tap j are even launched and land
+    // while the previous tap is stored / synchronised; G of the next tile is prefetched during the last tap.
+    WgRegs<8> RG;
+    WgRegs<NX> RX;
+    auto load_x = [&](int tile, int j) {
+        const int bb = tile / tiles_per_utt;
+        const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
+        wg_load<NX>(RX, q.Npad, p.X, p.ldx, p.Cin, bb, p.T, tt0, j * p.dil - p.padl, p.xmul, p.ldxmul);
+    };
+    auto store_x = [&](int slot) {
+        wg_store<SPLIT, NX>(RX, slot_hi[slot], slot_lo[slot], csx, q.Npad, p.pro_act, p.pro_slope, p.pro_scale);
+    };
+    auto load_g = [&](int tile) {
+        const int bb = tile / tiles_per_utt;
+        const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
+        wg_load<8>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
     };
 
+    if (tile_beg < tile_end) { load_g(tile_beg); load_x(tile_beg, 0); }
     for (int tile = tile_beg; tile < tile_end; ++tile) {
-        const int b = tile / tiles_per_utt;
-        const int t0 = (tile - b * tiles_per_utt) * CRK_WG_TF;
-        // G^T is read by every MMA of the previous tile: wait for them before overwriting it
+        if (tile == tile_beg) dbg_stamp(q.dbg, 0);
+        // G and first-tap X of this tile are already in registers (prefetched); wait for the previous
+        // tile's MMAs (they read the G^T buffer and the ring slot we are about to overwrite)
         if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
-        wg_stage_T<SPLIT>(Gh, Gl, CSG, 128, p.G, p.ldg, p.N, b, p.T, t0, 0, CRK_ACT_NONE, 0.f, 1.f, nullptr, 0);
-        // first tap's X^T (its slot was released by the tile-level wait above, or is fresh)
-        stage_x(tile, 0, step & 1);
+        if (tile == tile_beg) dbg_stamp(q.dbg, 1);
+        wg_store<SPLIT, 8>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
+        store_x(step & 1);
+        if (p.k > 1) load_x(tile, 1);                          // next tap's loads in flight during the sync + MMAs
+        else if (tile + 1 < tile_end) { load_g(tile + 1); load_x(tile + 1, 0); }
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
         __syncthreads();
         tc::tc_fence_after();
+        if (tile == tile_beg) dbg_stamp(q.dbg, 2);
         for (int j = 0; j < p.k; ++j, ++step) {
-            if (threadIdx.x == 0) {
+            if (threadIdx.x == 32) {
                 uint32_t acc = ntile_done > 0 ? 1u : 0u;
                 // A = G^T (M = 128 rows = co), B = X_j^T (N rows = ci), K = 64 frames
                 tc_issue_kmajor<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi[step & 1]),
@@ -168,22 +192,27 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams q) {
                 const int nstep = step + 1;
                 // slot (nstep&1) was last used by step nstep-2 (this tile or the previous one)
                 if (nstep >= 2) ok &= tc::mbar_wait(&bar_slot[nstep & 1], ((nstep - 2) >> 1) & 1);
-                stage_x(tile, j + 1, nstep & 1);
+                store_x(nstep & 1);                        // tap j+1 (loaded one tap ago)
+                if (j + 2 < p.k) load_x(tile, j + 2);      // prefetch the tap after
+                else if (tile + 1 < tile_end) { load_g(tile + 1); load_x(tile + 1, 0); }
                 tc::fence_proxy_async_smem();
                 __syncthreads();
             }
         }
+        if (tile == tile_beg) dbg_stamp(q.dbg, 3);
         ++ntile_done;
     }
+    dbg_stamp(q.dbg, 4);
     if (ntile_done > 0) ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1);
     tc::tc_fence_after();
     if (!ok) timeout_s = 1;
     __syncthreads();
+    dbg_stamp(q.dbg, 5);
 
     // ---- epilogue: D_j^T[co][ci] -> part[chunk][j][ci][co] ----
     const int co = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float* out = p.part + (size_t)blockIdx.x * p.k * p.Rows * q.TN;
+    float* out = p.part + (size_t)blockIdx.x * p.part_stride;
     const int nblk = (q.Npad + 31) >> 5;
     const float poison = __int_as_float(0x7fc00000);
     for (int j = 0; j < p.k; ++j)
@@ -200,6 +229,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams q) {
         }
     tc::tc_fence_before();
     __syncthreads();
+    dbg_stamp(q.dbg, 6);
     if (warp == 1) tc::tmem_dealloc<512>(tmem);
 }
 
@@ -208,7 +238,8 @@ inline size_t wgrad_tc_smem(int Npad, bool split) {
     return ((split ? 2 : 1) * g + (split ? 4 : 2) * x) * sizeof(float);
 }
 inline bool wgrad_tc_ok(const WgradParams& p, int TN, int Npad, bool split) {
-    return TN <= 128 && Npad >= 16 && Npad <= 128 && p.k * Npad <= 512 && p.Rows <= Npad &&
+    return TN <= 128 && Npad >= 16 && Npad <= 128 && p.k * Npad <= 512 && p.Rows <= Npad &&  // X^T tile <= 8 float4/thread
+          
            wgrad_tc_smem(Npad, split) <= 220 * 1024;
 }
 
@@ -222,17 +253,21 @@ inline WgradTcWork wgrad_tc_work(int B, int T) {
     return w;
 }
 
-template <bool SPLIT>
-inline cudaError_t launch_wgrad_tc_t(const WgradTcParams& q, int nchunk, cudaStream_t s) {
+template <bool SPLIT, int NX>
+inline cudaError_t launch_wgrad_tc_nx(const WgradTcParams& q, int nchunk, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<SPLIT, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     TimedLaunch tl(CRK_K_WGRAD, s);
-    k_wgrad_tc<SPLIT><<<nchunk, 256, wgrad_tc_smem(q.Npad, SPLIT), s>>>(q);
+    k_wgrad_tc<SPLIT, NX><<<nchunk, 256, wgrad_tc_smem(q.Npad, SPLIT), s>>>(q);
     return launch_check();
+}
+template <bool SPLIT>
+inline cudaError_t launch_wgrad_tc_t(const WgradTcParams& q, int nchunk, cudaStream_t s) {
+    return q.Npad <= 64 ? launch_wgrad_tc_nx<SPLIT, 4>(q, nchunk, s) : launch_wgrad_tc_nx<SPLIT, 8>(q, nchunk, s);
 }
 
 inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err) {
@@ -243,7 +278,7 @@ inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, in
     if (!wgrad_tc_ok(p, TN, Npad, split)) return false;
     const WgradTcWork w = wgrad_tc_work(p.B, p.T);
     WgradTcParams q;
-    q.p = p; q.p.part = part; q.p.tiles_per_chunk = w.tiles_per_chunk; q.TN = TN; q.Npad = Npad;
+    q.p = p; q.p.part = part; q.p.tiles_per_chunk = w.tiles_per_chunk; q.TN = TN; q.Npad = Npad; q.dbg = dbg_take(CRK_K_WGRAD);
     *nchunk = w.nchunk;
     *err = split ? launch_wgrad_tc_t<true>(q, w.nchunk, s) : launch_wgrad_tc_t<false>(q, w.nchunk, s);
     return true;

@@ -54,7 +54,7 @@ SIGNATURES = {
     "crk_version": (i32, []),
     "crk_set_precision": (i32, [i32]),
     "crk_get_precision": (i32, []),
-    "crk_debug_timestamps": (i32, [vp]),
+    "crk_debug_timestamps": (i32, [vp, i32, i32]),
     "crk_launch_count": (C.c_ulonglong, []),
     "crk_timing_enable": (i32, [i32]),
     "crk_timing_read": (i32, [C.POINTER(i32), C.POINTER(f32)]),

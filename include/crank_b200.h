@@ -44,9 +44,10 @@ int crk_get_precision(void);
  * timing of one kernel family (ids: 1 resblock_fwd, 2 wgrad, 3 conv, 4 resblock_bwd_gate, 5 vq_argmin;
  * 0 disables).  crk_timing_read synchronises the device and returns (#launches, total ms) since enable. */
 unsigned long long crk_launch_count(void);
-/* performance debugging: device buffer of gridDim*8 int64 that tensor-core kernels fill with clock64()
- * phase stamps (NULL disables) */
-int crk_debug_timestamps(long long* device_buffer);
+/* performance debugging: the `launch_index`-th launch (counted from this call) of tensor-core kernel
+ * family `kernel_id` (1 resblock_fwd, 2 wgrad, 3 conv) writes clock64() phase stamps into
+ * device_buffer[gridDim][16] (NULL disables) */
+int crk_debug_timestamps(long long* device_buffer, int kernel_id, int launch_index);
 int crk_timing_enable(int kernel_id);
 int crk_timing_read(int* count, float* total_ms);
 

@@ -1,27 +1,39 @@
-"""Per-phase clock64() breakdown of the tensor-core residual-block forward kernel (perf debugging)."""
-import ctypes as C, os, sys
+"""Per-phase clock64() breakdown of the tensor-core kernels (perf debugging): encoder-0 stack, 64 x 500 frames."""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from crank_b200 import lib as L
 from crank_b200.parallel_wavegan.models import ParallelWaveGANGenerator
 
-for prec in ("tf32x3", "tf32"):
-    L.set_precision(prec)
-    net = ParallelWaveGANGenerator(in_channels=80, out_channels=64, kernel_size=5, layers=8, stacks=4, aux_channels=0,
-                                   upsample_conditional_features=False).cuda()
-    B, T = 64, 500
-    x = torch.randn(B, T, 80, device="cuda")
-    ntiles = B * ((T + 127) // 128)
-    buf = torch.zeros(ntiles * 8, dtype=torch.int64, device="cuda")
-    with torch.no_grad():
-        for _ in range(3):
-            net.forward_cl(x)
-        L.check(L.lib().crk_debug_timestamps(buf.data_ptr()))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); net.forward_cl(x); e1.record(); torch.cuda.synchronize()
-        L.check(L.lib().crk_debug_timestamps(None))
-    t = buf.view(ntiles, 8)[:, :6].double().cpu()
+prec = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
+L.set_precision(prec)
+net = ParallelWaveGANGenerator(in_channels=80, out_channels=64, kernel_size=5, layers=8, stacks=4, aux_channels=0,
+                               upsample_conditional_features=False).cuda()
+B, T = 64, 500
+x = torch.randn(B, T, 80, device="cuda", requires_grad=True)
+buf = torch.zeros(1024 * 16, dtype=torch.int64, device="cuda")
+
+
+def run():
+    y = net.forward_cl(x)
+    y.square().mean().backward()
+    torch.cuda.synchronize()
+
+
+for _ in range(2):
+    run()
+# launch indices inside one fwd+bwd:  fwd TC: blocks 0..7 (idx 3 = k5 dil 2); conv TC: fwd first(0) head(1,2), bwd: head dgrads(3,4),
+# then per layer dgrad...; wgrad TC: head(0,1) then per layer: Wos(2), conv(3), ...
+sel = {"resblock_fwd k5 d2": (1, 3, ["stageX", "gemm1+TMA", "epi1", "gemm2+TaSb", "epi2"], 6),
+       "conv dgrad k5 (K128,N64)": (3, 5, ["stageA", "mma+TMA", "tmem->smem", "coalesced epilogue"], 5),
+       "wgrad conv k5": (2, 3, ["issue loads+wait", "store G,X0", "taps(tile0)", "other tiles", "wait last", "epilogue"], 7)}
+for name, (kid, idx, labels, n) in sel.items():
+    buf.zero_()
+    L.check(L.lib().crk_debug_timestamps(buf.data_ptr(), kid, idx))
+    run()
+    L.check(L.lib().crk_debug_timestamps(None, 0, 0))
+    t = buf.view(-1, 16)[:, :n].double().cpu()
+    t = t[t[:, 0] > 0]
     d = (t[:, 1:] - t[:, :-1]).mean(0)
-    names = ["stageX", "gemm1(taps,TMA)", "epi1(gate)", "gemm2", "epi2"]
-    print(prec, "stack fwd ms", e0.elapsed_time(e1), "| last block per-CTA cycles:", {n: int(v) for n, v in zip(names, d)},
-          "total", int((t[:, 5] - t[:, 0]).mean()), "span(all CTAs)", int(t[:, 5].max() - t[:, 0].min()))
+    print(prec, name, "CTAs", len(t), {l: int(v) for l, v in zip(labels, d)}, "total", int((t[:, n - 1] - t[:, 0]).mean()),
+          "kernel span", int(t[:, n - 1].max() - t[:, 0].min()))
