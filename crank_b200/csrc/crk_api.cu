@@ -67,8 +67,10 @@ int crk_timing_enable(int kernel_id) {
     }
     I.enabled_id = kernel_id;
     I.npairs = 0;
+    I.flops = 0.0;
     return CRK_OK;
 }
+double crk_timing_flops(void) { return instr().flops; }
 int crk_timing_read(int* count, float* total_ms) {
     Instr& I = instr();
     if (!count || !total_ms) return CRK_ERR_ARG;
@@ -208,7 +210,7 @@ int crk_vq_argmin(const float* x, int ldx, const float* W, const float* WT, cons
         API_TRY(cudaFuncSetAttribute(k_vq_argmin, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
-    TimedLaunch tl(CRK_K_VQ_ARGMIN, (cudaStream_t)stream);
+    TimedLaunch tl(CRK_K_VQ_ARGMIN, (cudaStream_t)stream, 2.0 * F * 64.0 * K);
     k_vq_argmin<<<(unsigned)cdivl(F, 64), CRK_THREADS, smem, (cudaStream_t)stream>>>(p);
     API_TRY(launch_check());
     return CRK_OK;

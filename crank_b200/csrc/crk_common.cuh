@@ -41,15 +41,17 @@ struct Instr {
     static const int kMaxPairs = 8192;
     cudaEvent_t* ev = nullptr;   // 2*kMaxPairs
     int npairs = 0;
+    double flops = 0.0;          // algorithmic FLOPs of the timed launches
 };
 inline Instr& instr() { static Instr i; return i; }
 inline cudaError_t launch_check() { ++instr().launches; return cudaGetLastError(); }
 struct TimedLaunch {   // RAII: records events around a launch when timing of `id` is on
     bool on; cudaStream_t s; int slot;
-    TimedLaunch(int id, cudaStream_t st) : on(false), s(st), slot(0) {
+    TimedLaunch(int id, cudaStream_t st, double flops = 0.0) : on(false), s(st), slot(0) {
         Instr& I = instr();
         if (I.enabled_id == id && I.ev && I.npairs < Instr::kMaxPairs) {
             on = true; slot = I.npairs++;
+            I.flops += flops;
             cudaEventRecord(I.ev[2 * slot], s);
         }
     }

@@ -155,7 +155,7 @@ inline cudaError_t launch_conv_t(const ConvParams& p, cudaStream_t s) {
         attr_set = true;
     }
     const int tiles = p.B * cdiv(p.T, CRK_TM);
-    TimedLaunch tl(CRK_K_CONV, s);
+    TimedLaunch tl(CRK_K_CONV, s, 2.0 * p.B * p.T * p.Cin * p.Cout * p.k);
     k_conv<CPT><<<tiles, CRK_THREADS, conv_smem_bytes(p, CPT), s>>>(p);
     return launch_check();
 }
@@ -277,30 +277,36 @@ __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ part, 
     }
 }
 
-// per-chunk column sums (bias gradients): part[chunk * stride + n], block = 2 row groups x 128 columns;
-// 4 independent accumulators per thread keep 4 loads in flight; fixed summation order.
-__global__ void __launch_bounds__(CRK_THREADS) k_colsum(const float* __restrict__ G, int ldg, int N,
-                                                         long long F, int rows_per_chunk,
-                                                         float* __restrict__ part, int TN, long long stride) {
-    __shared__ float red[128];
+// per-chunk column sums (bias gradients): part[chunk * stride + n].  block = 8 row groups x 128 columns
+// (1024 threads), 4 independent accumulators per thread: 32 rows in flight per column; the 8 group
+// sums are combined through shared memory in fixed order (deterministic).
+#define CRK_COLSUM_THREADS 1024
+__global__ void __launch_bounds__(CRK_COLSUM_THREADS) k_colsum(const float* __restrict__ G, int ldg, int N,
+                                                                long long F, int rows_per_chunk,
+                                                                float* __restrict__ part, int TN, long long stride) {
+    __shared__ float red[8][128];
     const int n = threadIdx.x & 127, g = threadIdx.x >> 7;
     const long long beg = (long long)blockIdx.x * rows_per_chunk;
     const long long end = min(F, beg + rows_per_chunk);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (n < N) {
         long long r = beg + g;
-        for (; r + 6 < end; r += 8) {
+        for (; r + 24 < end; r += 32) {
             s0 += __ldg(G + r * ldg + n);
-            s1 += __ldg(G + (r + 2) * ldg + n);
-            s2 += __ldg(G + (r + 4) * ldg + n);
-            s3 += __ldg(G + (r + 6) * ldg + n);
+            s1 += __ldg(G + (r + 8) * ldg + n);
+            s2 += __ldg(G + (r + 16) * ldg + n);
+            s3 += __ldg(G + (r + 24) * ldg + n);
         }
-        for (; r < end; r += 2) s0 += __ldg(G + r * ldg + n);
+        for (; r < end; r += 8) s0 += __ldg(G + r * ldg + n);
     }
-    const float s = (s0 + s1) + (s2 + s3);
-    if (g == 1) red[n] = s;
+    red[g][n] = (s0 + s1) + (s2 + s3);
     __syncthreads();
-    if (g == 0 && n < TN) part[(size_t)blockIdx.x * stride + n] = s + red[n];
+    if (g == 0 && n < TN) {
+        float s = red[0][n];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) s += red[i][n];
+        part[(size_t)blockIdx.x * stride + n] = s;
+    }
 }
 
 // Work-partition policy of wgrad: number of per-chunk partials so that the (chunk, tap, rowblock)
@@ -339,7 +345,7 @@ inline cudaError_t launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    TimedLaunch tl(CRK_K_WGRAD, s);
+    TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * p.B * p.T * p.Cin * p.N * p.k / (grid.z > 0 ? 1 : 1));
     k_wgrad<CPT><<<grid, CRK_THREADS, smem, s>>>(p);
     return launch_check();
 }
@@ -376,7 +382,7 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
     const long long F = (long long)p.B * p.T;
     if (fused_bias) {
         const int rows_per_chunk = (int)cdivl(F, nchunk);     // chunk c may be empty: it then writes zeros
-        k_colsum<<<nchunk, CRK_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part + nW, TN, stride);
+        k_colsum<<<nchunk, CRK_COLSUM_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part + nW, TN, stride);
         e = launch_check();
         if (e != cudaSuccess) return e;
     }
@@ -389,7 +395,7 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
         if (nch > nchunk) nch = nchunk;
         if (nch < 1) nch = 1;
         const int rows_per_chunk = (int)cdivl(F, nch);
-        k_colsum<<<nch, CRK_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part, TN, TN);
+        k_colsum<<<nch, CRK_COLSUM_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part, TN, TN);
         e = launch_check();
         if (e != cudaSuccess) return e;
         k_reduce<<<cdiv(TN, 128), 256, 0, s>>>(part, nch, TN, db, 0);

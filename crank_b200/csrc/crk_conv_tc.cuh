@@ -20,7 +20,55 @@ struct ConvTcParams {
     const float* Wtc;     // per tap: hi [Kpad/4][chunk_rows(Npad)][4] | lo [same]
     int Kpad, Npad;       // K rounded up to 8, UMMA N (multiple of 16, <= 128)
     int dbg;
+    // gate-backward mode (gate != 0), the tensor-core version of k_resblock_bwd_gate:
+    //   A[row][4q+r] = r<2 ? sqrt(.5)*dH[row][2q+r] : dS[row][2q+r-2]  (also written to GOS),  acc = A . Wos^T = dz
+    //   epilogue: dg = gate'(dz; ta, sb) -> DG (interleaved gate order),  z = ta*sb -> Z
+    int gate;
+    const float* g_dH; const float* g_dS; const float* g_TaSb;
+    float* g_DG; float* g_GOS; float* g_Z;
 };
+
+// A-tile staging of the gate-backward mode: 128 rows x 128 interleaved [sqrt(.5)*dH | dS] columns
+template <bool SPLIT>
+__device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats, const ConvTcParams& q, int b, int t0) {
+    const ConvParams& p = q.p;
+    constexpr int U = 4;
+    const int total = CRK_TC_TM * 32;                      // (row, pair q): one float4 of A each
+    for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
+        float2 h[U], sg[U];
+        int rr[U], qq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + u * blockDim.x;
+            rr[u] = idx >> 5; qq[u] = idx & 31;
+            h[u] = make_float2(0.f, 0.f); sg[u] = make_float2(0.f, 0.f);
+            const int t = t0 + rr[u];
+            if (idx < total && t < p.T) {
+                const size_t row = (size_t)b * p.T + t;
+                if (q.g_dH) h[u] = __ldg(reinterpret_cast<const float2*>(q.g_dH + row * 64) + qq[u]);
+                sg[u] = __ldg(reinterpret_cast<const float2*>(q.g_dS + row * 64) + qq[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + u * blockDim.x;
+            if (idx >= total) continue;
+            const float4 v = make_float4(h[u].x * CRK_SQRT_HALF, h[u].y * CRK_SQRT_HALF, sg[u].x, sg[u].y);
+            const int t = t0 + rr[u];
+            if (t < p.T) reinterpret_cast<float4*>(q.g_GOS + ((size_t)b * p.T + t) * 128)[qq[u]] = v;
+            const int off = qq[u] * cs_floats + rr[u] * 4;  // chunk = pair index (4 interleaved columns)
+            if (SPLIT) {
+                float4 hh, ll;
+                tc::split_tf32(v.x, hh.x, ll.x); tc::split_tf32(v.y, hh.y, ll.y);
+                tc::split_tf32(v.z, hh.z, ll.z); tc::split_tf32(v.w, hh.w, ll.w);
+                *reinterpret_cast<float4*>(hi + off) = hh;
+                *reinterpret_cast<float4*>(lo + off) = ll;
+            } else {
+                *reinterpret_cast<float4*>(hi + off) = v;
+            }
+        }
+    }
+}
 
 template <bool SPLIT, int U>
 __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_floats, const ConvParams& p, int Kpad,
@@ -144,7 +192,8 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
         for (int st = 0; st < 2 && st < nsteps; ++st) produce(st);
     // (deeper batches were measured: no gain in the 3xTF32 mode, and the extra registers cost the plain
     //  TF32 variant its second resident CTA per SM, which matters far more)
-    tc_stage_act_pro<SPLIT, 4>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
+    if (q.gate) tc_stage_gos<SPLIT>(Xh, Xl, csx, q, b, t0);
+    else tc_stage_act_pro<SPLIT, 4>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
     tc::fence_proxy_async_smem();
     __syncthreads();
     dbg_stamp(q.dbg, 1);
@@ -202,7 +251,35 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     }
     __syncthreads();
     dbg_stamp(q.dbg, 3);
-    {
+    if (q.gate) {
+        // lanes over gate pairs (2 z channels each): TaSb read and DG write are one float4 per lane
+        const int nlive = min(CRK_TC_TM, p.T - t0);
+        const size_t row0 = (size_t)b * p.T + t0;
+        const int total = nlive * 32;
+        constexpr int U = 4;
+        for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * U) {
+            float4 ts[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e < total) ts[u] = __ldg(reinterpret_cast<const float4*>(q.g_TaSb + (row0 + (e >> 5)) * 128) + (e & 31));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e >= total) continue;
+                const int rr = e >> 5, qi = e & 31;
+                const float dz0 = S[rr * sst + 2 * qi], dz1 = S[rr * sst + 2 * qi + 1];
+                float4 dg;
+                dg.x = (dz0 * ts[u].z) * (1.f - ts[u].x * ts[u].x);
+                dg.y = (dz1 * ts[u].w) * (1.f - ts[u].y * ts[u].y);
+                dg.z = (dz0 * ts[u].x) * ((1.f - ts[u].z) * ts[u].z);
+                dg.w = (dz1 * ts[u].y) * ((1.f - ts[u].w) * ts[u].w);
+                reinterpret_cast<float4*>(q.g_DG + (row0 + rr) * 128)[qi] = dg;
+                reinterpret_cast<float2*>(q.g_Z + (row0 + rr) * 64)[qi] = make_float2(ts[u].x * ts[u].z, ts[u].y * ts[u].w);
+            }
+        }
+    } else {
         const int nlive = min(CRK_TC_TM, p.T - t0);
         const size_t row0 = (size_t)b * p.T + t0;
         const int total = nlive * p.Cout;
@@ -244,7 +321,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     tc::tc_fence_before();
     __syncthreads();
     dbg_stamp(q.dbg, 4);
-    if (timeout_s && threadIdx.x == 0) p.Y[((size_t)b * p.T + t0) * p.ldy] = __int_as_float(0x7fc00000);
+    if (timeout_s && threadIdx.x == 0) (q.gate ? q.g_DG : p.Y)[((size_t)b * p.T + t0) * (q.gate ? 128 : p.ldy)] = __int_as_float(0x7fc00000);
     if (warp == 1) tc::tmem_dealloc<128>(tmem);
 }
 
@@ -271,7 +348,7 @@ inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
         attr_set = true;
     }
     const int tiles = q.p.B * cdiv(q.p.T, CRK_TC_TM);
-    TimedLaunch tl(CRK_K_CONV, s);
+    TimedLaunch tl(CRK_K_CONV, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.Cout * q.p.k);
     ConvTcParams qq = q;
     qq.dbg = dbg_take(CRK_K_CONV);
     k_conv_tc<SPLIT><<<tiles, 256, conv_tc_smem(q, SPLIT), s>>>(qq);
@@ -283,11 +360,38 @@ inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc,
     const int mode = precision_mode();
     if (mode != CRK_PREC_FP32) {
         ConvTcParams q;
-        q.p = p; q.Wtc = wtc; q.Kpad = kpad; q.Npad = npad; q.dbg = 0;
+        q.p = p; q.Wtc = wtc; q.Kpad = kpad; q.Npad = npad; q.dbg = 0; q.gate = 0;
+        q.g_dH = q.g_dS = q.g_TaSb = nullptr; q.g_DG = q.g_GOS = q.g_Z = nullptr;
         const bool split = mode == CRK_PREC_TF32X3;
         if (conv_tc_ok(q, split)) return split ? launch_conv_tc_t<true>(q, s) : launch_conv_tc_t<false>(q, s);
     }
     return launch_conv(p, cpt, s);
+}
+
+// tensor-core gate backward (replaces k_resblock_bwd_gate when a tensor-core mode is on)
+inline bool gate_bwd_tc(const ResBwdGateParams& g, const float* wos_tct, cudaStream_t s, cudaError_t* err) {
+    const int mode = precision_mode();
+    if (mode == CRK_PREC_FP32) return false;
+    ConvTcParams q;
+    q.p = conv_params_default();
+    q.p.B = g.B; q.p.T = g.T; q.p.Cin = 128; q.p.Cout = 64; q.p.k = 1; q.p.dil = 1; q.p.padl = 0;
+    q.Wtc = wos_tct; q.Kpad = 128; q.Npad = 64; q.dbg = 0; q.gate = 1;
+    q.g_dH = g.dH; q.g_dS = g.dS; q.g_TaSb = g.TaSb; q.g_DG = g.DG; q.g_GOS = g.GOS; q.g_Z = g.Z;
+    const bool split = mode == CRK_PREC_TF32X3;
+    if (conv_tc_smem(q, split) > 220 * 1024) return false;
+    if (split) {
+        static bool a1 = false;
+        if (!a1) { *err = cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); if (*err) return true; a1 = true; }
+        TimedLaunch tl(CRK_K_BWD_GATE, s, 2.0 * g.B * g.T * 128.0 * 64);
+        k_conv_tc<true><<<g.B * cdiv(g.T, CRK_TC_TM), 256, conv_tc_smem(q, true), s>>>(q);
+    } else {
+        static bool a2 = false;
+        if (!a2) { *err = cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); if (*err) return true; a2 = true; }
+        TimedLaunch tl(CRK_K_BWD_GATE, s, 2.0 * g.B * g.T * 128.0 * 64);
+        k_conv_tc<false><<<g.B * cdiv(g.T, CRK_TC_TM), 256, conv_tc_smem(q, false), s>>>(q);
+    }
+    *err = launch_check();
+    return true;
 }
 
 }  // namespace crk

@@ -126,7 +126,7 @@ inline cudaError_t launch_resblock_fwd(const ResFwdParams& p, cudaStream_t s) {
         attr_set = true;
     }
     const int tiles = p.B * cdiv(p.T, CRK_TM);
-    TimedLaunch tl(CRK_K_RESBLOCK_FWD, s);
+    TimedLaunch tl(CRK_K_RESBLOCK_FWD, s, 2.0 * p.B * p.T * (64.0 * 128 * p.k + p.Ca * 128.0 + 64.0 * 128));
     k_resblock_fwd<<<tiles, CRK_THREADS, resblock_fwd_smem(p.k, p.dil, p.CaPad), s>>>(p);
     return launch_check();
 }
@@ -206,7 +206,7 @@ inline cudaError_t launch_resblock_bwd_gate(const ResBwdGateParams& p, cudaStrea
         attr_set = true;
     }
     const int tiles = p.B * cdiv(p.T, CRK_TM);
-    TimedLaunch tl(CRK_K_BWD_GATE, s);
+    TimedLaunch tl(CRK_K_BWD_GATE, s, 2.0 * p.B * p.T * 128.0 * 64);
     k_resblock_bwd_gate<<<tiles, CRK_THREADS, smem, s>>>(p);
     return launch_check();
 }

@@ -379,7 +379,7 @@ inline cudaError_t launch_resblock_fwd_tc(const ResFwdTcParams& q, cudaStream_t 
         attr_set = true;
     }
     const int tiles = q.p.B * cdiv(q.p.T, CRK_TC_TM);
-    TimedLaunch tl(CRK_K_RESBLOCK_FWD, s);
+    TimedLaunch tl(CRK_K_RESBLOCK_FWD, s, 2.0 * q.p.B * q.p.T * (64.0 * 128 * q.p.k + q.p.Ca * 128.0 + 64.0 * 128));
     ResFwdTcParams qq = q;
     qq.dbg = dbg_take(CRK_K_RESBLOCK_FWD);
     k_resblock_fwd_tc<SPLIT><<<tiles, 256, resblock_fwd_tc_smem(q.p.k, q.p.dil), s>>>(qq);

@@ -370,7 +370,9 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
             p.dH = dh_cur; p.dS = ws + W.ds; p.TaSb = act + A.tasb + (long long)l * F * 128;
             p.WosT = weff + L.tab.d[L.out[l]].wt_off;
             p.DG = ws + W.dg; p.GOS = ws + W.gos; p.Z = ws + W.z; p.B = B; p.T = T;
-            CRK_TRY(launch_resblock_bwd_gate(p, s));
+            cudaError_t ge = cudaSuccess;
+            if (gate_bwd_tc(p, weff + L.tab.d[L.out[l]].tct_off, s, &ge)) CRK_TRY(ge);
+            else CRK_TRY(launch_resblock_bwd_gate(p, s));
         }
         {   // [out|skip] weights:  dWos = z^T . gos
             const crk_conv_desc& d = L.tab.d[L.out[l]];

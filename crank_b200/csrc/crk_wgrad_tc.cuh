@@ -261,7 +261,7 @@ inline cudaError_t launch_wgrad_tc_nx(const WgradTcParams& q, int nchunk, cudaSt
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    TimedLaunch tl(CRK_K_WGRAD, s);
+    TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
     k_wgrad_tc<SPLIT, NX><<<nchunk, 256, wgrad_tc_smem(q.Npad, SPLIT), s>>>(q);
     return launch_check();
 }

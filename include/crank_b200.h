@@ -50,6 +50,8 @@ unsigned long long crk_launch_count(void);
 int crk_debug_timestamps(long long* device_buffer, int kernel_id, int launch_index);
 int crk_timing_enable(int kernel_id);
 int crk_timing_read(int* count, float* total_ms);
+/* algorithmic FLOPs (2*MACs of the real, unpadded contraction) of the launches timed since crk_timing_enable */
+double crk_timing_flops(void);
 
 /* tcgen05 probe: single-CTA TF32 GEMM through the tensor-core kernels' operand layout / descriptors /
  * TMEM path.  mode 0: D[m][n] = sum_k A[row_shift+m][k]*B[n][k]  (K-major operands, any row shift);
