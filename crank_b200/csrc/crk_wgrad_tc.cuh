@@ -24,6 +24,7 @@ struct WgradTcParams {
     int TN;            // packed columns of G / dW (32*cpt)
     int Npad;          // UMMA N = round_up(Cin, 16)
     int dbg;
+    int nslot;         // X^T ring depth (2..4): hides the MMA completion latency of the per-tap handshake
 };
 
 // Transposed staging of src[frame t0+shift .. +64)[0..ncols):  elem(frame f, channel c) -> (f>>2)*cs + c*4 + (f&3).
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     const WgradParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
-    __shared__ uint64_t bar_slot[2];
+    __shared__ uint64_t bar_slot[4];
     __shared__ uint64_t bar_tile;
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
@@ -119,8 +120,10 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     float* Gl = Gh + KCH * CSG;
     float* ring = Gl + (SPLIT ? KCH * CSG : 0);
     const int xhalf = KCH * csx;
-    float* slot_hi[2] = {ring, ring + (SPLIT ? 2 : 1) * xhalf};
-    float* slot_lo[2] = {ring + xhalf, ring + 3 * xhalf};
+    const int slot_floats = (SPLIT ? 2 : 1) * xhalf;
+    const int NS = q.nslot;
+    auto slot_hi = [&](int sl) -> float* { return ring + sl * slot_floats; };
+    auto slot_lo = [&](int sl) -> float* { return ring + sl * slot_floats + xhalf; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int tiles_per_utt = (p.T + CRK_WG_TF - 1) / CRK_WG_TF;
@@ -129,7 +132,8 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     const int tile_end = min(ntiles, tile_beg + p.tiles_per_chunk);
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(&bar_slot[0], 1); tc::mbar_init(&bar_slot[1], 1); tc::mbar_init(&bar_tile, 1);
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&bar_slot[i], 1);
+        tc::mbar_init(&bar_tile, 1);
         tc::fence_mbar_init();
         timeout_s = 0;
     }
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
         wg_load<NX>(RX, q.Npad, p.X, p.ldx, p.Cin, bb, p.T, tt0, j * p.dil - p.padl, p.xmul, p.ldxmul);
     };
     auto store_x = [&](int slot) {
-        wg_store<SPLIT, NX>(RX, slot_hi[slot], slot_lo[slot], csx, q.Npad, p.pro_act, p.pro_slope, p.pro_scale);
+        wg_store<SPLIT, NX>(RX, slot_hi(slot), slot_lo(slot), csx, q.Npad, p.pro_act, p.pro_slope, p.pro_scale);
     };
     auto load_g = [&](int tile) {
         const int bb = tile / tiles_per_utt;
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
         if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
         if (tile == tile_beg) dbg_stamp(q.dbg, 1);
         wg_store<SPLIT, 8>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
-        store_x(step & 1);
+        store_x(step % NS);
         if (p.k > 1) load_x(tile, 1);                          // next tap's loads in flight during the sync + MMAs
         else if (tile + 1 < tile_end) { load_g(tile + 1); load_x(tile + 1, 0); }
         tc::fence_proxy_async_smem();
@@ -183,16 +187,17 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
             if (threadIdx.x == 32) {
                 uint32_t acc = ntile_done > 0 ? 1u : 0u;
                 // A = G^T (M = 128 rows = co), B = X_j^T (N rows = ci), K = 64 frames
-                tc_issue_kmajor<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi[step & 1]),
-                                       tc::smem_u32(slot_lo[step & 1]), csx * 4, CRK_WG_TF, idesc, acc);
-                tc::umma_commit(&bar_slot[step & 1]);
+                tc_issue_kmajor<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi(step % NS)),
+                                       tc::smem_u32(slot_lo(step % NS)), csx * 4, CRK_WG_TF, idesc, acc);
+                tc::umma_commit(&bar_slot[step % NS]);
                 if (j == p.k - 1) tc::umma_commit(&bar_tile);
             }
             if (j + 1 < p.k) {
                 const int nstep = step + 1;
-                // slot (nstep&1) was last used by step nstep-2 (this tile or the previous one)
-                if (nstep >= 2) ok &= tc::mbar_wait(&bar_slot[nstep & 1], ((nstep - 2) >> 1) & 1);
-                store_x(nstep & 1);                        // tap j+1 (loaded one tap ago)
+                // slot (nstep % NS) was last used by step nstep-NS (this tile or the previous one): with
+                // NS slots the MMAs of the last NS-1 taps may still be in flight while we store
+                if (nstep >= NS) ok &= tc::mbar_wait(&bar_slot[nstep % NS], ((nstep - NS) / NS) & 1);
+                store_x(nstep % NS);                       // tap j+1 (loaded one tap ago)
                 if (j + 2 < p.k) load_x(tile, j + 2);      // prefetch the tap after
                 else if (tile + 1 < tile_end) { load_g(tile + 1); load_x(tile + 1, 0); }
                 tc::fence_proxy_async_smem();
@@ -233,9 +238,14 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     if (warp == 1) tc::tmem_dealloc<512>(tmem);
 }
 
+inline int wgrad_tc_nslot(int Npad, bool split) {
+    const size_t g = (size_t)16 * 129 * 4 * (split ? 2 : 1), x = (size_t)16 * tc::chunk_rows(Npad) * 4 * (split ? 2 : 1);
+    size_t n = (200 * 1024 / sizeof(float) - g) / x;
+    return n >= 4 ? 4 : (n >= 3 ? 3 : 2);
+}
 inline size_t wgrad_tc_smem(int Npad, bool split) {
     const size_t g = (size_t)16 * 129 * 4, x = (size_t)16 * tc::chunk_rows(Npad) * 4;
-    return ((split ? 2 : 1) * g + (split ? 4 : 2) * x) * sizeof(float);
+    return ((split ? 2 : 1) * g + (split ? 2 : 1) * wgrad_tc_nslot(Npad, split) * x) * sizeof(float);
 }
 inline bool wgrad_tc_ok(const WgradParams& p, int TN, int Npad, bool split) {
     return TN <= 128 && Npad >= 16 && Npad <= 128 && p.k * Npad <= 512 && p.Rows <= Npad &&  // X^T tile <= 8 float4/thread
@@ -278,7 +288,7 @@ inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, in
     if (!wgrad_tc_ok(p, TN, Npad, split)) return false;
     const WgradTcWork w = wgrad_tc_work(p.B, p.T);
     WgradTcParams q;
-    q.p = p; q.p.part = part; q.p.tiles_per_chunk = w.tiles_per_chunk; q.TN = TN; q.Npad = Npad; q.dbg = dbg_take(CRK_K_WGRAD);
+    q.p = p; q.p.part = part; q.p.tiles_per_chunk = w.tiles_per_chunk; q.TN = TN; q.Npad = Npad; q.dbg = dbg_take(CRK_K_WGRAD); q.nslot = wgrad_tc_nslot(Npad, split);
     *nchunk = w.nchunk;
     *err = split ? launch_wgrad_tc_t<true>(q, w.nchunk, s) : launch_wgrad_tc_t<false>(q, w.nchunk, s);
     return true;
