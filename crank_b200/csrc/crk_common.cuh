@@ -62,6 +62,9 @@ struct TimedLaunch {   // RAII: records events around a launch when timing of `i
 // accuracy) or plain TF32 on the tcgen05 tensor cores.  Process-wide; set by crk_set_precision().
 enum { CRK_PREC_FP32 = 0, CRK_PREC_TF32X3 = 1, CRK_PREC_TF32 = 2 };
 inline int& precision_mode() { static int m = CRK_PREC_FP32; return m; }
+// debugging: bit mask of tensor-core kernel families forced back to the fp32 kernels
+// (1 fused forward, 2 conv/dgrad, 4 wgrad, 8 gate backward)
+inline int& tc_disable_mask() { static int m = 0; return m; }
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }

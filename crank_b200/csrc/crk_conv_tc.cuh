@@ -358,7 +358,7 @@ inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
 // precision-aware dispatch: tensor cores when enabled and the shape fits, else the fp32 kernel
 inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc, int kpad, int npad, cudaStream_t s) {
     const int mode = precision_mode();
-    if (mode != CRK_PREC_FP32) {
+    if (mode != CRK_PREC_FP32 && !(tc_disable_mask() & 2)) {
         ConvTcParams q;
         q.p = p; q.Wtc = wtc; q.Kpad = kpad; q.Npad = npad; q.dbg = 0; q.gate = 0;
         q.g_dH = q.g_dS = q.g_TaSb = nullptr; q.g_DG = q.g_GOS = q.g_Z = nullptr;
@@ -371,7 +371,7 @@ inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc,
 // tensor-core gate backward (replaces k_resblock_bwd_gate when a tensor-core mode is on)
 inline bool gate_bwd_tc(const ResBwdGateParams& g, const float* wos_tct, cudaStream_t s, cudaError_t* err) {
     const int mode = precision_mode();
-    if (mode == CRK_PREC_FP32) return false;
+    if (mode == CRK_PREC_FP32 || (tc_disable_mask() & 8)) return false;
     ConvTcParams q;
     q.p = conv_params_default();
     q.p.B = g.B; q.p.T = g.T; q.p.Cin = 128; q.p.Cout = 64; q.p.k = 1; q.p.dil = 1; q.p.padl = 0;

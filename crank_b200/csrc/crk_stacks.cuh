@@ -274,7 +274,7 @@ inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float*
         p.TaSb = act + A.tasb + (long long)l * F * 128;
         p.B = B; p.T = T; p.k = c->kernel_size; p.dil = dil; p.padl = wn_padl(c, dil);
         const int mode = precision_mode();
-        if (mode == CRK_PREC_FP32 || (c->kernel_size - 1) * dil > 16) {
+        if (mode == CRK_PREC_FP32 || (tc_disable_mask() & 1) || (c->kernel_size - 1) * dil > 16) {
             CRK_TRY(launch_resblock_fwd(p, s));
         } else {
             ResFwdTcParams q;

@@ -282,7 +282,7 @@ inline cudaError_t launch_wgrad_tc_t(const WgradTcParams& q, int nchunk, cudaStr
 
 inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err) {
     const int mode = precision_mode();
-    if (mode == CRK_PREC_FP32) return false;
+    if (mode == CRK_PREC_FP32 || (tc_disable_mask() & 4)) return false;
     const bool split = mode == CRK_PREC_TF32X3;
     const int Npad = round_up(p.Cin, 16);
     if (!wgrad_tc_ok(p, TN, Npad, split)) return false;

@@ -54,6 +54,7 @@ SIGNATURES = {
     "crk_version": (i32, []),
     "crk_set_precision": (i32, [i32]),
     "crk_get_precision": (i32, []),
+    "crk_debug_tc_disable": (i32, [i32]),
     "crk_debug_timestamps": (i32, [vp, i32, i32]),
     "crk_launch_count": (C.c_ulonglong, []),
     "crk_timing_enable": (i32, [i32]),

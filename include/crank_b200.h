@@ -39,6 +39,9 @@ int crk_version(void);
  * tcgen05 tensor cores (error-compensated, ~fp32 accuracy: the parity mode), 2 = plain TF32 (fast mode). */
 int crk_set_precision(int mode);
 int crk_get_precision(void);
+/* debugging: force tensor-core kernel families back to the fp32 kernels
+ * (bit 1 fused forward, 2 conv/dgrad, 4 wgrad, 8 gate backward) */
+int crk_debug_tc_disable(int mask);
 
 /* instrumentation: number of kernels the library has launched in this process; optional CUDA-event
  * timing of one kernel family (ids: 1 resblock_fwd, 2 wgrad, 3 conv, 4 resblock_bwd_gate, 5 vq_argmin;
