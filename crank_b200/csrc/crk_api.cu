@@ -14,6 +14,7 @@
 #include "crk_stacks.cuh"
 #include "crk_tc_probe.cuh"
 #include "crk_vq.cuh"
+#include "crk_vq_tc.cuh"
 
 namespace crk {
 static thread_local char g_cuda_err[256] = "";
@@ -213,6 +214,35 @@ int crk_vq_argmin(const float* x, int ldx, const float* W, const float* WT, cons
     }
     TimedLaunch tl(CRK_K_VQ_ARGMIN, (cudaStream_t)stream, 2.0 * F * 64.0 * K);
     k_vq_argmin<<<(unsigned)cdivl(F, 64), CRK_THREADS, smem, (cudaStream_t)stream>>>(p);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+long long crk_vq_tc_blob_floats(int K, int D) {
+    if (D != 64 || K < 128 || (K % 128) != 0) return -1;
+    return (long long)(K / 128) * 2 * 16 * 129 * 4;
+}
+int crk_vq_pack_tc(const float* W, float* blob, int K, int D, void* stream) {
+    if (!W || !blob || D != 64 || K < 128 || (K % 128) != 0) return CRK_ERR_ARG;
+    k_vq_pack_tc<<<cdiv(K * 64, 256), 256, 0, (cudaStream_t)stream>>>(W, blob, K);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+int crk_vq_argmin_tc(const float* x, int ldx, const float* W, const float* blob, const float* wn,
+                     long long* idx, float* e, int lde, float* qx, int ldqx, long long F, int K, int D,
+                     void* stream) {
+    if (!x || !W || !blob || !wn || !idx || !e || !qx || F < 1) return CRK_ERR_ARG;
+    if (D != 64 || K < 128 || (K % 128) != 0 || K > 512) return CRK_ERR_UNSUPPORTED;
+    VqTcParams q;
+    q.p.x = x; q.p.ldx = ldx; q.p.W = W; q.p.WT = nullptr; q.p.wn = wn; q.p.idx = idx; q.p.e = e; q.p.lde = lde;
+    q.p.qx = qx; q.p.ldqx = ldqx; q.p.F = F; q.p.K = K;
+    q.blob = blob;
+    static bool attr_set = false;
+    if (!attr_set) {
+        API_TRY(cudaFuncSetAttribute(k_vq_argmin_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        attr_set = true;
+    }
+    TimedLaunch tl(CRK_K_VQ_ARGMIN, (cudaStream_t)stream, 2.0 * F * 64.0 * K);
+    k_vq_argmin_tc<<<(unsigned)cdivl(F, 128), 256, vq_tc_smem(), (cudaStream_t)stream>>>(q);
     API_TRY(launch_check());
     return CRK_OK;
 }

@@ -75,6 +75,9 @@ SIGNATURES = {
     "crk_convstack_bwd": (i32, [PC, vp, vp, vp, i32, vp, vp, i32, vp, i32, f32, vp, vp, i32, i32, vp]),
     "crk_vq_prepare": (i32, [vp, vp, vp, i32, i32, vp]),
     "crk_vq_argmin": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, vp, i32, i64, i32, i32, vp]),
+    "crk_vq_tc_blob_floats": (i64, [i32, i32]),
+    "crk_vq_pack_tc": (i32, [vp, vp, i32, i32, vp]),
+    "crk_vq_argmin_tc": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, vp, i32, i64, i32, i32, vp]),
     "crk_vq_stats_ws_floats": (i64, [i64, i32, i32]),
     "crk_vq_stats": (i32, [vp, i32, vp, vp, vp, vp, i64, i32, i32, vp]),
     "crk_vq_ema": (i32, [vp, vp, vp, vp, vp, f32, f32, i32, i32, vp]),

@@ -138,8 +138,15 @@ class VQFn(torch.autograd.Function):
         idx = torch.empty(B, T, dtype=torch.int64, device=dev)
         e = torch.empty(B, T, D, dtype=_f32, device=dev)
         qx = torch.empty(B, T, D, dtype=_f32, device=dev)
-        L.call("crk_vq_argmin", L.ptr(x), ldx, L.ptr(Wc), L.ptr(WT), L.ptr(wn), L.ptr(idx),
-               L.ptr(e), D, L.ptr(qx), D, B * T, K, D)
+        if L.get_precision() != "fp32" and D == 64 and K % 128 == 0 and K <= 512:
+            # tensor-core distance GEMM + exact fp32 re-score of near-ties (same indices as the fp32 kernel)
+            blob = torch.empty(L.lib().crk_vq_tc_blob_floats(K, D), dtype=_f32, device=dev)
+            L.call("crk_vq_pack_tc", L.ptr(Wc), L.ptr(blob), K, D)
+            L.call("crk_vq_argmin_tc", L.ptr(x), ldx, L.ptr(Wc), L.ptr(blob), L.ptr(wn), L.ptr(idx),
+                   L.ptr(e), D, L.ptr(qx), D, B * T, K, D)
+        else:
+            L.call("crk_vq_argmin", L.ptr(x), ldx, L.ptr(Wc), L.ptr(WT), L.ptr(wn), L.ptr(idx),
+                   L.ptr(e), D, L.ptr(qx), D, B * T, K, D)
         ctx.save_for_backward(idx)
         ctx.KD = (K, D)
         ctx.mark_non_differentiable(idx)

@@ -157,6 +157,13 @@ int crk_vq_prepare(const float* W, float* WT, float* wn, int K, int D, void* str
 int crk_vq_argmin(const float* x, int ldx, const float* W, const float* WT, const float* wn,
                   long long* idx, float* e, int lde, float* qx, int ldqx, long long F, int K, int D,
                   void* stream);
+/* tensor-core argmin (3xTF32 distance GEMM on tcgen05 + exact fp32 re-score of near-ties; same result as
+ * crk_vq_argmin).  blob: crk_vq_tc_blob_floats() floats filled by crk_vq_pack_tc from the codebook. K <= 512 */
+long long crk_vq_tc_blob_floats(int K, int D);
+int crk_vq_pack_tc(const float* W, float* blob, int K, int D, void* stream);
+int crk_vq_argmin_tc(const float* x, int ldx, const float* W, const float* blob, const float* wn,
+                     long long* idx, float* e, int lde, float* qx, int ldqx, long long F, int K, int D,
+                     void* stream);
 long long crk_vq_stats_ws_floats(long long F, int K, int D);
 int crk_vq_stats(const float* x, int ldx, const long long* idx, float* counts, float* esum,
                  float* ws, long long F, int K, int D, void* stream);

@@ -37,7 +37,8 @@ def test_tensor_core_and_cuda_core_kernels_agree_at_full_size(lib_precision, B, 
     # Forward outputs must agree to 1e-4.  Gradients go through ReLU'(skip-sum) / ReLU'(head) masks: a
     # pre-activation within ~1e-5 of zero flips its mask between two implementations that agree to 1e-5
     # (measured: ~1 per 1e5 values), which changes the gradient of THAT frame by O(1).  So gradients are
-    # compared frame-wise: all but a small fraction of frames within 1e-4, and the parameter gradient
+    # compared frame-wise (one flip reaches +-34 frames through the 8 dilated dgrads): all but a few
+    # percent of the frames within 1e-4, and the parameter gradient
     # (a sum over frames) within 1e-2.
     def rel(a, b_):
         return ((a - b_).abs().max() / a.abs().max()).item()
@@ -50,7 +51,7 @@ def test_tensor_core_and_cuda_core_kernels_agree_at_full_size(lib_precision, B, 
     for n, a, b_ in (("dx", dx_f, dx_t), ("dc", dc_f, dc_t)):
         rowerr = (a - b_).abs().amax(dim=-1) / a.abs().max()
         frac = (rowerr > 1e-4).float().mean().item()
-        assert frac < 5e-3, f"{n}: {frac:.2%} of frames differ by more than 1e-4 at B={B}, T={T}"
+        assert frac < 5e-2, f"{n}: {frac:.2%} of frames differ by more than 1e-4 at B={B}, T={T}"
     assert rel(dth_f, dth_t) < 1e-2, f"dtheta differs by {rel(dth_f, dth_t):.2e}"
 
 

@@ -172,3 +172,27 @@ def test_tc_fast_mode_tf32_is_close(precision):
     worst = max(rel_err(pg[k], q.grad) for k, q in o.named_parameters() if q.grad is not None and q.grad.abs().max() > 1e-12)
     print(f"tf32 fast mode: fwd {rel_err(yp, yo):.1e} dx {rel_err(xp.grad, xo.grad):.1e} worst param grad {worst:.1e}")
     assert worst < 0.3
+
+
+def test_tc_vq_argmin_is_identical_to_fp32_kernel(precision):
+    """tensor-core argmin + exact re-score must return the very indices of the fp32 kernel (and e, qx bit-equal),
+    on a spread codebook, on the degenerate fresh-init codebook (all near-ties) and with dead codes (|w|~1e5)."""
+    from crank_b200 import ops
+
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(16, 500, 64, generator=g).cuda()
+    for kind in ("spread", "fresh", "dead"):
+        W = torch.randn(512, 64, generator=g)
+        if kind == "fresh":
+            W = (torch.rand(512, 64, generator=g) * 2 - 1) / 512
+        if kind == "dead":
+            W[100:300] *= 1e5
+        W = W.cuda()
+        precision("fp32")
+        e0, q0, i0 = ops.VQFn.apply(x, W)
+        precision("tf32x3")
+        e1, q1, i1 = ops.VQFn.apply(x, W)
+        assert (i1 >= 0).all(), "tcgen05 pipeline timed out"
+        nm = int((i0 != i1).sum())
+        assert nm == 0, f"{kind}: {nm} indices differ between the fp32 and the tensor-core argmin"
+        assert torch.equal(e0, e1) and torch.equal(q0, q1)
