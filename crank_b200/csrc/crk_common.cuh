@@ -66,6 +66,37 @@ inline int& precision_mode() { static int m = CRK_PREC_FP32; return m; }
 // (1 fused forward, 2 conv/dgrad, 4 wgrad, 8 gate backward)
 inline int& tc_disable_mask() { static int m = 0; return m; }
 
+// debugging / A-B switches for optional optimisations (crk_debug_opt_mask):
+//   1 programmatic dependent launch off, 2 bias column sums fused into k_wgrad_tc off,
+//   4 vectorised k_conv_tc epilogue off, 8 raw-tile k_wgrad_tc_raw off
+inline int& opt_disable_mask() { static int m = 0; return m; }
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// The steps of a stack are hundreds of short dependent kernels on one stream.  A kernel launched with
+// the programmatic-stream-serialisation attribute may become resident while its predecessor's last
+// wave is still running (every predecessor CTA has executed pdl_trigger() or exited): block
+// scheduling, barrier init and the TMEM allocation then overlap the predecessor's tail instead of
+// following its drain.  Contract kept by every kernel launched through launch_pdl(): NO global memory
+// access before pdl_wait() (which returns once the predecessor grid has completed and its writes are
+// visible), so the result is identical to plain stream order.  Both instructions are no-ops in a
+// kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    if (!(opt_disable_mask() & 1)) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long cdivl(long long a, long long b) { return (a + b - 1) / b; }

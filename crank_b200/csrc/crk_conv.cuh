@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(CRK_THREADS) k_wgrad(const WgradParams p) {
 __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ part, int nchunk, int n,
                                                 float* __restrict__ out, int accumulate) {
     __shared__ float4 red[8][32];
+    pdl_trigger();
+    pdl_wait();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int e = (blockIdx.x * 32 + tx) * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -285,6 +287,8 @@ __global__ void __launch_bounds__(CRK_COLSUM_THREADS) k_colsum(const float* __re
                                                                 long long F, int rows_per_chunk,
                                                                 float* __restrict__ part, int TN, long long stride) {
     __shared__ float red[8][128];
+    pdl_trigger();
+    pdl_wait();
     const int n = threadIdx.x & 127, g = threadIdx.x >> 7;
     const long long beg = (long long)blockIdx.x * rows_per_chunk;
     const long long end = min(F, beg + rows_per_chunk);
@@ -351,7 +355,8 @@ inline cudaError_t launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t 
 }
 
 // tensor-core path (defined in crk_wgrad_tc.cuh): returns true when it handled the partials
-bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err);
+bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err,
+                  bool fused_bias, bool* bias_done);
 
 // dW (and db when non-null) of one convolution.  cpt gives the packing of the G columns (TN=32*cpt).
 // dW and db must be adjacent (db == dW + k*Rows*TN, the packed weff layout) so that ONE deterministic
@@ -366,7 +371,8 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
     p.part_stride = stride;
     cudaError_t e = cudaSuccess;
     int nchunk = 0;
-    if (!wgrad_tc_try(p, TN, part, s, &nchunk, &e)) {
+    bool bias_done = false;
+    if (!wgrad_tc_try(p, TN, part, s, &nchunk, &e, fused_bias, &bias_done)) {
         const WgradWork w = wgrad_work(p.B, p.T, p.k, p.Rows);
         nchunk = w.nchunk;
         p.tiles_per_chunk = w.tiles_per_chunk;
@@ -380,14 +386,17 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
     }
     if (e != cudaSuccess) return e;
     const long long F = (long long)p.B * p.T;
-    if (fused_bias) {
+    if (fused_bias && !bias_done) {
         const int rows_per_chunk = (int)cdivl(F, nchunk);     // chunk c may be empty: it then writes zeros
-        k_colsum<<<nchunk, CRK_COLSUM_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part + nW, TN, stride);
+        e = launch_pdl(k_colsum, dim3(nchunk), dim3(CRK_COLSUM_THREADS), 0, s, p.G, p.ldg, p.N, F, rows_per_chunk,
+                       part + nW, TN, stride);
+        if (e != cudaSuccess) return e;
         e = launch_check();
         if (e != cudaSuccess) return e;
     }
     const int n = (int)stride;
-    k_reduce<<<cdiv(n, 128), 256, 0, s>>>(part, nchunk, n, dW, 0);
+    e = launch_pdl(k_reduce, dim3(cdiv(n, 128)), dim3(256), 0, s, (const float*)part, nchunk, n, dW, 0);
+    if (e != cudaSuccess) return e;
     e = launch_check();
     if (e != cudaSuccess) return e;
     if (db && !fused_bias) {
@@ -395,10 +404,13 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
         if (nch > nchunk) nch = nchunk;
         if (nch < 1) nch = 1;
         const int rows_per_chunk = (int)cdivl(F, nch);
-        k_colsum<<<nch, CRK_COLSUM_THREADS, 0, s>>>(p.G, p.ldg, p.N, F, rows_per_chunk, part, TN, TN);
+        e = launch_pdl(k_colsum, dim3(nch), dim3(CRK_COLSUM_THREADS), 0, s, p.G, p.ldg, p.N, F, rows_per_chunk, part, TN,
+                       (long long)TN);
+        if (e != cudaSuccess) return e;
         e = launch_check();
         if (e != cudaSuccess) return e;
-        k_reduce<<<cdiv(TN, 128), 256, 0, s>>>(part, nch, TN, db, 0);
+        e = launch_pdl(k_reduce, dim3(cdiv(TN, 128)), dim3(256), 0, s, (const float*)part, nch, TN, db, 0);
+        if (e != cudaSuccess) return e;
         e = launch_check();
     }
     return e;

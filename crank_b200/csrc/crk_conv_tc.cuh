@@ -20,6 +20,7 @@ struct ConvTcParams {
     const float* Wtc;     // per tap: hi [Kpad/4][chunk_rows(Npad)][4] | lo [same]
     int Kpad, Npad;       // K rounded up to 8, UMMA N (multiple of 16, <= 128)
     int dbg;
+    int vec_epi;          // epilogue may use 128-bit accesses (Cout, row strides and pointers all 16 B aligned)
     // gate-backward mode (gate != 0), the tensor-core version of k_resblock_bwd_gate:
     //   A[row][4q+r] = r<2 ? sqrt(.5)*dH[row][2q+r] : dS[row][2q+r-2]  (also written to GOS),  acc = A . Wos^T = dz
     //   epilogue: dg = gate'(dz; ta, sb) -> DG (interleaved gate order),  z = ta*sb -> Z
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
+    pdl_trigger();
     const int tiles_per_utt = (p.T + CRK_TC_TM - 1) / CRK_TC_TM;
     const int b = blockIdx.x / tiles_per_utt;
     const int t0 = (blockIdx.x - b * tiles_per_utt) * CRK_TC_TM;
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     bool ok = true;
+    pdl_wait();
     dbg_stamp(q.dbg, 0);
     if (threadIdx.x == 0)
         for (int st = 0; st < 2 && st < nsteps; ++st) produce(st);
@@ -279,6 +282,57 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
                 reinterpret_cast<float2*>(q.g_Z + (row0 + rr) * 64)[qi] = make_float2(ts[u].x * ts[u].z, ts[u].y * ts[u].w);
             }
         }
+    } else if (q.vec_epi) {
+        // 128-bit epilogue: one float4 (4 output channels of a frame) per thread per slot, U slots in
+        // flight, so the side inputs of a whole 128 x 64 tile (dgrad: residual grad + dropout
+        // multiplier) need 1-2 global round trips instead of 8
+        const int nlive = min(CRK_TC_TM, p.T - t0);
+        const size_t row0 = (size_t)b * p.T + t0;
+        const int c4n = p.Cout >> 2;
+        const int total = nlive * c4n;
+        constexpr int U = SPLIT ? 8 : 4;                    // (the 2-CTA/SM plain-TF32 variant is capped at 128 registers)
+        const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * U) {
+            float4 mulv[U], rv[U], dv[U], oldv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * blockDim.x;
+                mulv[u] = one4; rv[u] = zero4; dv[u] = one4; oldv[u] = zero4;
+                if (e < total) {
+                    const int rr = e / c4n, c4 = e - rr * c4n;
+                    const size_t row = row0 + rr;
+                    if (p.mul_src) mulv[u] = __ldg(reinterpret_cast<const float4*>(p.mul_src + row * p.ldmul) + c4);
+                    if (p.R) rv[u] = __ldg(reinterpret_cast<const float4*>(p.R + row * p.ldr) + c4);
+                    if (p.dact_src) dv[u] = __ldg(reinterpret_cast<const float4*>(p.dact_src + row * p.lddact) + c4);
+                    if (p.accumulate) oldv[u] = *(reinterpret_cast<const float4*>(p.Y + row * p.ldy) + c4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e >= total) continue;
+                const int rr = e / c4n, c4 = e - rr * c4n;
+                const float* sp = S + rr * sst + 4 * c4;
+                float y[4] = {sp[0], sp[1], sp[2], sp[3]};
+                const float m4[4] = {mulv[u].x, mulv[u].y, mulv[u].z, mulv[u].w};
+                const float r4[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+                const float d4[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+                const float o4[4] = {oldv[u].x, oldv[u].y, oldv[u].z, oldv[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float v = y[i];                     // same operation order as the scalar path below
+                    if (p.bias) v += __ldg(p.bias + 4 * c4 + i);
+                    v = apply_act(v, p.epi_act, p.epi_slope);
+                    v *= m4[i];
+                    v += p.rscale * r4[i];
+                    if (p.dact_src) v *= act_grad(d4[i], p.dact_mode, p.dact_slope);
+                    v *= p.out_scale;
+                    v += o4[i];
+                    y[i] = v;
+                }
+                reinterpret_cast<float4*>(p.Y + (row0 + rr) * p.ldy)[c4] = make_float4(y[0], y[1], y[2], y[3]);
+            }
+        }
     } else {
         const int nlive = min(CRK_TC_TM, p.T - t0);
         const size_t row0 = (size_t)b * p.T + t0;
@@ -351,7 +405,8 @@ inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
     TimedLaunch tl(CRK_K_CONV, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.Cout * q.p.k);
     ConvTcParams qq = q;
     qq.dbg = dbg_take(CRK_K_CONV);
-    k_conv_tc<SPLIT><<<tiles, 256, conv_tc_smem(q, SPLIT), s>>>(qq);
+    cudaError_t le = launch_pdl(k_conv_tc<SPLIT>, dim3(tiles), dim3(256), conv_tc_smem(q, SPLIT), s, qq);
+    if (le != cudaSuccess) return le;
     return launch_check();
 }
 
@@ -361,6 +416,9 @@ inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc,
     if (mode != CRK_PREC_FP32 && !(tc_disable_mask() & 2)) {
         ConvTcParams q;
         q.p = p; q.Wtc = wtc; q.Kpad = kpad; q.Npad = npad; q.dbg = 0; q.gate = 0;
+        auto al = [](const float* ptr, int ld) { return ptr == nullptr || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)); };
+        q.vec_epi = !(opt_disable_mask() & 4) && (p.Cout & 3) == 0 && p.Y != nullptr && al(p.Y, p.ldy) && al(p.mul_src, p.ldmul) &&
+                    al(p.R, p.ldr) && al(p.dact_src, p.lddact);
         q.g_dH = q.g_dS = q.g_TaSb = nullptr; q.g_DG = q.g_GOS = q.g_Z = nullptr;
         const bool split = mode == CRK_PREC_TF32X3;
         if (conv_tc_ok(q, split)) return split ? launch_conv_tc_t<true>(q, s) : launch_conv_tc_t<false>(q, s);
@@ -375,7 +433,7 @@ inline bool gate_bwd_tc(const ResBwdGateParams& g, const float* wos_tct, cudaStr
     ConvTcParams q;
     q.p = conv_params_default();
     q.p.B = g.B; q.p.T = g.T; q.p.Cin = 128; q.p.Cout = 64; q.p.k = 1; q.p.dil = 1; q.p.padl = 0;
-    q.Wtc = wos_tct; q.Kpad = 128; q.Npad = 64; q.dbg = 0; q.gate = 1;
+    q.Wtc = wos_tct; q.Kpad = 128; q.Npad = 64; q.dbg = 0; q.gate = 1; q.vec_epi = 0;
     q.g_dH = g.dH; q.g_dS = g.dS; q.g_TaSb = g.TaSb; q.g_DG = g.DG; q.g_GOS = g.GOS; q.g_Z = g.Z;
     const bool split = mode == CRK_PREC_TF32X3;
     if (conv_tc_smem(q, split) > 220 * 1024) return false;
@@ -383,12 +441,14 @@ inline bool gate_bwd_tc(const ResBwdGateParams& g, const float* wos_tct, cudaStr
         static bool a1 = false;
         if (!a1) { *err = cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); if (*err) return true; a1 = true; }
         TimedLaunch tl(CRK_K_BWD_GATE, s, 2.0 * g.B * g.T * 128.0 * 64);
-        k_conv_tc<true><<<g.B * cdiv(g.T, CRK_TC_TM), 256, conv_tc_smem(q, true), s>>>(q);
+        *err = launch_pdl(k_conv_tc<true>, dim3(g.B * cdiv(g.T, CRK_TC_TM)), dim3(256), conv_tc_smem(q, true), s, q);
+        if (*err) return true;
     } else {
         static bool a2 = false;
         if (!a2) { *err = cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); if (*err) return true; a2 = true; }
         TimedLaunch tl(CRK_K_BWD_GATE, s, 2.0 * g.B * g.T * 128.0 * 64);
-        k_conv_tc<false><<<g.B * cdiv(g.T, CRK_TC_TM), 256, conv_tc_smem(q, false), s>>>(q);
+        *err = launch_pdl(k_conv_tc<false>, dim3(g.B * cdiv(g.T, CRK_TC_TM)), dim3(256), conv_tc_smem(q, false), s, q);
+        if (*err) return true;
     }
     *err = launch_check();
     return true;

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
+    pdl_trigger();                                      // the next kernel may start its prologue
     const int tiles_per_utt = (p.T + CRK_TC_TM - 1) / CRK_TC_TM;
     const int b = blockIdx.x / tiles_per_utt;
     const int t0 = (blockIdx.x - b * tiles_per_utt) * CRK_TC_TM;
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     bool ok = true;
+    pdl_wait();                                         // predecessor complete: global memory may be touched
     dbg_stamp(q.dbg, 0);
 
     // ---- producer: first two blobs in flight while everybody stages the activation tile ----
@@ -382,7 +384,8 @@ inline cudaError_t launch_resblock_fwd_tc(const ResFwdTcParams& q, cudaStream_t 
     TimedLaunch tl(CRK_K_RESBLOCK_FWD, s, 2.0 * q.p.B * q.p.T * (64.0 * 128 * q.p.k + q.p.Ca * 128.0 + 64.0 * 128));
     ResFwdTcParams qq = q;
     qq.dbg = dbg_take(CRK_K_RESBLOCK_FWD);
-    k_resblock_fwd_tc<SPLIT><<<tiles, 256, resblock_fwd_tc_smem(q.p.k, q.p.dil), s>>>(qq);
+    cudaError_t le = launch_pdl(k_resblock_fwd_tc<SPLIT>, dim3(tiles), dim3(256), resblock_fwd_tc_smem(q.p.k, q.p.dil), s, qq);
+    if (le != cudaSuccess) return le;
     return launch_check();
 }
 

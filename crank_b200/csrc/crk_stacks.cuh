@@ -41,6 +41,8 @@ struct DescTable {
 // packed fwd layout W[j][ci][pcol] and the transposed tap-flipped layout WT[k-1-j][pcol][ci].
 __global__ void __launch_bounds__(128) k_weightnorm_fwd(const DescTable tab, const float* __restrict__ theta,
                                                          float* __restrict__ weff) {
+    pdl_trigger();
+    pdl_wait();
     const crk_conv_desc d = tab.d[blockIdx.y];
     const int co = blockIdx.x;
     if (co >= d.cout) return;
@@ -85,6 +87,8 @@ __global__ void __launch_bounds__(128) k_weightnorm_fwd(const DescTable tab, con
 __global__ void __launch_bounds__(128) k_weightnorm_bwd(const DescTable tab, const float* __restrict__ theta,
                                                          const float* __restrict__ gweff,
                                                          float* __restrict__ gtheta) {
+    pdl_trigger();
+    pdl_wait();
     const crk_conv_desc d = tab.d[blockIdx.y];
     const int co = blockIdx.x;
     if (co >= d.cout) return;
@@ -125,14 +129,16 @@ __global__ void __launch_bounds__(128) k_weightnorm_bwd(const DescTable tab, con
 inline cudaError_t launch_weightnorm(const DescTable& tab, const float* theta, float* weff, cudaStream_t s) {
     int maxc = 1;
     for (int i = 0; i < tab.n; ++i) maxc = tab.d[i].cout > maxc ? tab.d[i].cout : maxc;
-    k_weightnorm_fwd<<<dim3(maxc, tab.n), 128, 0, s>>>(tab, theta, weff);
+    cudaError_t e = launch_pdl(k_weightnorm_fwd, dim3(maxc, tab.n), dim3(128), 0, s, tab, theta, weff);
+    if (e != cudaSuccess) return e;
     return launch_check();
 }
 inline cudaError_t launch_weightnorm_bwd(const DescTable& tab, const float* theta, const float* gweff,
                                          float* gtheta, cudaStream_t s) {
     int maxc = 1;
     for (int i = 0; i < tab.n; ++i) maxc = tab.d[i].cout > maxc ? tab.d[i].cout : maxc;
-    k_weightnorm_bwd<<<dim3(maxc, tab.n), 128, 0, s>>>(tab, theta, gweff, gtheta);
+    cudaError_t e = launch_pdl(k_weightnorm_bwd, dim3(maxc, tab.n), dim3(128), 0, s, tab, theta, gweff, gtheta);
+    if (e != cudaSuccess) return e;
     return launch_check();
 }
 

@@ -25,6 +25,8 @@ struct WgradTcParams {
     int Npad;          // UMMA N = round_up(Cin, 16)
     int dbg;
     int nslot;         // X^T ring depth (2..4): hides the MMA completion latency of the per-tap handshake
+    int bias;          // != 0: also write the per-chunk column sums of G (bias-gradient partial) behind the
+                       // chunk's [k][Rows][TN] block, i.e. what k_colsum would have produced in a second pass over G
 };
 
 // Transposed staging of src[frame t0+shift .. +64)[0..ncols):  elem(frame f, channel c) -> (f>>2)*cs + c*4 + (f&3).
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
+    pdl_trigger();
     constexpr int KCH = CRK_WG_TF / 4;                     // 16 frame chunks per tile
     constexpr int CSG = 129 * 4;                           // G^T: 128 rows -> 129
     const int csx = tc::chunk_rows(q.Npad) * 4;
@@ -153,6 +156,13 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     // while the previous tap is stored / synchronised; G of the next tile is prefetched during the last tap.
     WgRegs<8> RG;
     WgRegs<NX> RX;
+    // bias gradient: every G element passes through this thread's registers exactly once (wg_load of the
+    // tile), always the same (frame f = tid & 63, channel quad tid/64 + 4u) slot -> per-thread running
+    // sums, combined once per CTA in fixed order (deterministic); no second pass over G
+    float4 bsum[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) bsum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();
     auto load_x = [&](int tile, int j) {
         const int bb = tile / tiles_per_utt;
         const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
@@ -175,6 +185,12 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
         if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
         if (tile == tile_beg) dbg_stamp(q.dbg, 1);
         wg_store<SPLIT, 8>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
+        if (q.bias) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                bsum[u].x += RG.v[u].x; bsum[u].y += RG.v[u].y; bsum[u].z += RG.v[u].z; bsum[u].w += RG.v[u].w;
+            }
+        }
         store_x(step % NS);
         if (p.k > 1) load_x(tile, 1);                          // next tap's loads in flight during the sync + MMAs
         else if (tile + 1 < tile_end) { load_g(tile + 1); load_x(tile + 1, 0); }
@@ -232,10 +248,308 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
                     out[((size_t)j * p.Rows + ci) * q.TN + co] = timeout_s ? poison : (ntile_done > 0 ? v[i] : 0.f);
             }
         }
+    if (q.bias) {
+        // frames live on the 64 threads that share tid/64: warp-shuffle sum over 32 frames, then the two
+        // warps of a pair through shared memory (all MMAs have completed: the G^T buffer is free)
+        float* red = smem;                                 // [8 warps][32]
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float c4[4] = {bsum[u].x, bsum[u].y, bsum[u].z, bsum[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float sv = c4[e];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                if (lane == 0) red[warp * 32 + u * 4 + e] = sv;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < q.TN) {
+            const int c = threadIdx.x;                     // G column: quad c/4 = g + 4u (g = tid/64 of its owners)
+            const int quad = c >> 2, g = quad & 3, u = quad >> 2;
+            const float sv = red[(2 * g) * 32 + u * 4 + (c & 3)] + red[(2 * g + 1) * 32 + u * 4 + (c & 3)];
+            out[(size_t)p.k * p.Rows * q.TN + c] = timeout_s ? poison : sv;
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
     dbg_stamp(q.dbg, 6);
     if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
+// ---- raw-tile variant (k > 1) --------------------------------------------------------------------
+// The k tap tiles of one 64-frame tile are the SAME (64 + halo) input rows shifted by j*dil frames.
+// k_wgrad_tc fetches each of them from global memory (k latency-bound round trips per tile, one per
+// tap iteration); here the rows are fetched ONCE per tile (register-prefetched a whole tile ahead),
+// parked row-major in shared memory with the prologue applied, and every tap's transposed hi/lo
+// operand tile is produced from that copy (shared -> shared).
+//   xraw[r][c]  (row stride Npad + 4 floats: the 128-bit reads of 8 consecutive rows hit 8 distinct
+//   bank groups), r <-> input time t0 - padl + r, zero outside [0, T).
+template <int NR>
+__device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, const float* __restrict__ src, int ld,
+                                            int ncols, int b, int T, int tstart, const float* __restrict__ mul, int ldmul) {
+    const int total = rows * c4n;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                     (mul == nullptr || (((ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mul) & 15) == 0)));
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+        const int idx = threadIdx.x + u * 256;
+        R.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        R.m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (idx < total) {
+            const int r = idx / c4n, c4 = idx - r * c4n;
+            const int c = c4 * 4;
+            const int tt = tstart + r;
+            if (tt >= 0 && tt < T && c < ncols) {
+                const size_t row = (size_t)b * T + tt;
+                if (vec && c + 3 < ncols) {
+                    R.v[u] = __ldg(reinterpret_cast<const float4*>(src + row * ld + c));
+                    if (mul) R.m[u] = __ldg(reinterpret_cast<const float4*>(mul + row * ldmul + c));
+                } else {
+                    float t4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (c + e < ncols) {
+                            t4[e] = __ldg(src + row * ld + c + e);
+                            if (mul) m4[e] = __ldg(mul + row * ldmul + c + e);
+                        }
+                    R.v[u] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                    R.m[u] = make_float4(m4[0], m4[1], m4[2], m4[3]);
+                }
+            }
+        }
+    }
+}
+
+template <int NR>
+__device__ __forceinline__ void wg_store_raw(const WgRegs<NR>& R, float* xraw, int stride, int c4n, int rows,
+                                             int pro_act, float pro_slope, float pro_scale) {
+    const int total = rows * c4n;
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+        const int idx = threadIdx.x + u * 256;
+        if (idx >= total) continue;
+        const int r = idx / c4n, c4 = idx - r * c4n;
+        float4 x;
+        x.x = apply_act(R.v[u].x * pro_scale, pro_act, pro_slope) * R.m[u].x;
+        x.y = apply_act(R.v[u].y * pro_scale, pro_act, pro_slope) * R.m[u].y;
+        x.z = apply_act(R.v[u].z * pro_scale, pro_act, pro_slope) * R.m[u].z;
+        x.w = apply_act(R.v[u].w * pro_scale, pro_act, pro_slope) * R.m[u].w;
+        *reinterpret_cast<float4*>(xraw + r * stride + c4 * 4) = x;
+    }
+}
+
+// transposed hi/lo operand tile of one tap from the raw rows: elem(frame f, channel c) = xraw[f + shift][c]
+template <bool SPLIT, int NX>
+__device__ __forceinline__ void wg_transpose_raw(const float* xraw, int stride, float* hi, float* lo, int cs_floats,
+                                                 int nrows_pad, int shift) {
+    const int total = CRK_WG_TF * (nrows_pad >> 2);
+#pragma unroll
+    for (int u = 0; u < NX; ++u) {
+        const int idx = threadIdx.x + u * 256;
+        if (idx >= total) continue;
+        const int c4 = idx >> 6, f = idx & 63;
+        const float4 v = *reinterpret_cast<const float4*>(xraw + (f + shift) * stride + c4 * 4);
+        const int off = (f >> 2) * cs_floats + c4 * 16 + (f & 3);
+        const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (SPLIT) {
+                float h, l;
+                tc::split_tf32(x[e], h, l);
+                hi[off + e * 4] = h;
+                lo[off + e * 4] = l;
+            } else {
+                hi[off + e * 4] = x[e];
+            }
+        }
+    }
+}
+
+template <bool SPLIT, int NX>
+__global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) {
+    constexpr int NR = NX == 4 ? 6 : 10;                   // raw-tile float4 per thread (host checks the fit)
+    const WgradParams& p = q.p;
+    extern __shared__ float4 crk_smem4[];
+    float* smem = reinterpret_cast<float*>(crk_smem4);
+    __shared__ uint64_t bar_slot[4];
+    __shared__ uint64_t bar_tile;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int timeout_s;
+
+    pdl_trigger();
+    constexpr int KCH = CRK_WG_TF / 4;
+    constexpr int CSG = 129 * 4;
+    const int csx = tc::chunk_rows(q.Npad) * 4;
+    float* Gh = smem;
+    float* Gl = Gh + KCH * CSG;
+    float* ring = Gl + (SPLIT ? KCH * CSG : 0);
+    const int xhalf = KCH * csx;
+    const int slot_floats = (SPLIT ? 2 : 1) * xhalf;
+    const int NS = q.nslot;
+    float* xraw = ring + NS * slot_floats;
+    const int rstride = q.Npad + 4;
+    const int c4n = q.Npad >> 2;
+    const int rows_raw = CRK_WG_TF + (p.k - 1) * p.dil;
+    auto slot_hi = [&](int sl) -> float* { return ring + sl * slot_floats; };
+    auto slot_lo = [&](int sl) -> float* { return ring + sl * slot_floats + xhalf; };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int tiles_per_utt = (p.T + CRK_WG_TF - 1) / CRK_WG_TF;
+    const int ntiles = p.B * tiles_per_utt;
+    const int tile_beg = blockIdx.x * p.tiles_per_chunk;
+    const int tile_end = min(ntiles, tile_beg + p.tiles_per_chunk);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&bar_slot[i], 1);
+        tc::mbar_init(&bar_tile, 1);
+        tc::fence_mbar_init();
+        timeout_s = 0;
+    }
+    if (warp == 1) tc::tmem_alloc<512>(&tmem_base_s);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
+    const uint32_t gh_s = tc::smem_u32(Gh), gl_s = tc::smem_u32(Gl);
+    bool ok = true;
+    int step = 0;
+    int ntile_done = 0;
+
+    WgRegs<8> RG;
+    WgRegs<NR> RX;
+    float4 bsum[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) bsum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();
+    auto load_tile = [&](int tile) {
+        const int bb = tile / tiles_per_utt;
+        const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
+        wg_load<8>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
+        wg_load_raw<NR>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
+    };
+
+    if (tile_beg < tile_end) load_tile(tile_beg);
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+        if (tile == tile_beg) dbg_stamp(q.dbg, 0);
+        // previous tile's MMAs read the G^T buffer and the ring slots; every thread has also passed the
+        // barrier that follows the previous tile's last transposition, so xraw may be overwritten
+        if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
+        if (tile == tile_beg) dbg_stamp(q.dbg, 1);
+        wg_store<SPLIT, 8>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
+        if (q.bias) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                bsum[u].x += RG.v[u].x; bsum[u].y += RG.v[u].y; bsum[u].z += RG.v[u].z; bsum[u].w += RG.v[u].w;
+            }
+        }
+        wg_store_raw<NR>(RX, xraw, rstride, c4n, rows_raw, p.pro_act, p.pro_slope, p.pro_scale);
+        if (tile + 1 < tile_end) load_tile(tile + 1);      // a whole tile (k tap iterations) of latency cover
+        __syncthreads();
+        if (tile == tile_beg) dbg_stamp(q.dbg, 2);
+        for (int j = 0; j < p.k; ++j, ++step) {
+            const int sl = step % NS;
+            // the MMAs of step - NS (this tile; earlier tiles are covered by bar_tile) read this slot
+            if (j >= NS) ok &= tc::mbar_wait(&bar_slot[sl], ((step - NS) / NS) & 1);
+            wg_transpose_raw<SPLIT, NX>(xraw, rstride, slot_hi(sl), slot_lo(sl), csx, q.Npad, j * p.dil);
+            tc::fence_proxy_async_smem();
+            tc::tc_fence_before();
+            __syncthreads();
+            tc::tc_fence_after();
+            if (threadIdx.x == 32) {
+                uint32_t acc = ntile_done > 0 ? 1u : 0u;
+                tc_issue_kmajor<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi(sl)),
+                                       tc::smem_u32(slot_lo(sl)), csx * 4, CRK_WG_TF, idesc, acc);
+                tc::umma_commit(&bar_slot[sl]);
+                if (j == p.k - 1) tc::umma_commit(&bar_tile);
+            }
+        }
+        if (tile == tile_beg) dbg_stamp(q.dbg, 3);
+        ++ntile_done;
+    }
+    dbg_stamp(q.dbg, 4);
+    if (ntile_done > 0) ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1);
+    tc::tc_fence_after();
+    if (!ok) timeout_s = 1;
+    __syncthreads();
+    dbg_stamp(q.dbg, 5);
+
+    // ---- epilogue (identical to k_wgrad_tc) ----
+    const int co = (warp & 3) * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* out = p.part + (size_t)blockIdx.x * p.part_stride;
+    const int nblk = (q.Npad + 31) >> 5;
+    const float poison = __int_as_float(0x7fc00000);
+    for (int j = 0; j < p.k; ++j)
+        for (int blk = warp >> 2; blk < nblk; blk += 2) {
+            float v[32];
+            if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
+            if (co >= q.TN) continue;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int ci = blk * 32 + i;
+                if (ci < p.Rows)
+                    out[((size_t)j * p.Rows + ci) * q.TN + co] = timeout_s ? poison : (ntile_done > 0 ? v[i] : 0.f);
+            }
+        }
+    if (q.bias) {
+        float* red = smem;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float c4[4] = {bsum[u].x, bsum[u].y, bsum[u].z, bsum[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float sv = c4[e];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                if (lane == 0) red[warp * 32 + u * 4 + e] = sv;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < q.TN) {
+            const int c = threadIdx.x;
+            const int quad = c >> 2, g = quad & 3, u = quad >> 2;
+            const float sv = red[(2 * g) * 32 + u * 4 + (c & 3)] + red[(2 * g + 1) * 32 + u * 4 + (c & 3)];
+            out[(size_t)p.k * p.Rows * q.TN + c] = timeout_s ? poison : sv;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    dbg_stamp(q.dbg, 6);
+    if (warp == 1) tc::tmem_dealloc<512>(tmem);
+}
+
+// raw-tile variant: shared-memory plan and applicability
+inline size_t wgrad_raw_floats(int Npad, int k, int dil) { return (size_t)(CRK_WG_TF + (k - 1) * dil) * (Npad + 4); }
+inline int wgrad_raw_nslot(int Npad, int k, int dil, bool split) {
+    const size_t g = (size_t)16 * 129 * 4 * (split ? 2 : 1), x = (size_t)16 * tc::chunk_rows(Npad) * 4 * (split ? 2 : 1);
+    const size_t budget = 200 * 1024 / sizeof(float);
+    const size_t fixed = g + wgrad_raw_floats(Npad, k, dil);
+    if (fixed + 2 * x > budget) return 0;
+    const size_t n = (budget - fixed) / x;
+    return n >= 4 ? 4 : (int)n;
+}
+inline bool wgrad_raw_ok(const WgradParams& p, int Npad, bool split) {
+    if (p.k < 2 || (opt_disable_mask() & 8)) return false;
+    const int nr = Npad <= 64 ? 6 : 10;
+    if ((CRK_WG_TF + (p.k - 1) * p.dil) * (Npad >> 2) > nr * 256) return false;
+    return wgrad_raw_nslot(Npad, p.k, p.dil, split) >= 2;
+}
+template <bool SPLIT, int NX>
+inline cudaError_t launch_wgrad_tc_raw_nx(const WgradTcParams& q, int nchunk, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc_raw<SPLIT, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const size_t g = (size_t)16 * 129 * 4 * (SPLIT ? 2 : 1), x = (size_t)16 * tc::chunk_rows(q.Npad) * 4 * (SPLIT ? 2 : 1);
+    const size_t smem = (g + q.nslot * x + wgrad_raw_floats(q.Npad, q.p.k, q.p.dil)) * sizeof(float);
+    TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
+    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX>, dim3(nchunk), dim3(256), smem, s, q);
+    if (le != cudaSuccess) return le;
+    return launch_check();
 }
 
 inline int wgrad_tc_nslot(int Npad, bool split) {
@@ -272,7 +586,8 @@ inline cudaError_t launch_wgrad_tc_nx(const WgradTcParams& q, int nchunk, cudaSt
         attr_set = true;
     }
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
-    k_wgrad_tc<SPLIT, NX><<<nchunk, 256, wgrad_tc_smem(q.Npad, SPLIT), s>>>(q);
+    cudaError_t le = launch_pdl(k_wgrad_tc<SPLIT, NX>, dim3(nchunk), dim3(256), wgrad_tc_smem(q.Npad, SPLIT), s, q);
+    if (le != cudaSuccess) return le;
     return launch_check();
 }
 template <bool SPLIT>
@@ -280,7 +595,10 @@ inline cudaError_t launch_wgrad_tc_t(const WgradTcParams& q, int nchunk, cudaStr
     return q.Npad <= 64 ? launch_wgrad_tc_nx<SPLIT, 4>(q, nchunk, s) : launch_wgrad_tc_nx<SPLIT, 8>(q, nchunk, s);
 }
 
-inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err) {
+// fused_bias: the caller wants the bias-gradient partial behind each chunk's weight partial; *bias_done
+// tells it whether this kernel produced it (else k_colsum must run)
+inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err,
+                         bool fused_bias, bool* bias_done) {
     const int mode = precision_mode();
     if (mode == CRK_PREC_FP32 || (tc_disable_mask() & 4)) return false;
     const bool split = mode == CRK_PREC_TF32X3;
@@ -289,7 +607,15 @@ inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, in
     const WgradTcWork w = wgrad_tc_work(p.B, p.T);
     WgradTcParams q;
     q.p = p; q.p.part = part; q.p.tiles_per_chunk = w.tiles_per_chunk; q.TN = TN; q.Npad = Npad; q.dbg = dbg_take(CRK_K_WGRAD); q.nslot = wgrad_tc_nslot(Npad, split);
+    q.bias = (fused_bias && !(opt_disable_mask() & 2)) ? 1 : 0;
+    *bias_done = q.bias != 0;
     *nchunk = w.nchunk;
+    if (wgrad_raw_ok(p, Npad, split)) {
+        q.nslot = wgrad_raw_nslot(Npad, p.k, p.dil, split);
+        if (split) *err = Npad <= 64 ? launch_wgrad_tc_raw_nx<true, 4>(q, w.nchunk, s) : launch_wgrad_tc_raw_nx<true, 8>(q, w.nchunk, s);
+        else *err = Npad <= 64 ? launch_wgrad_tc_raw_nx<false, 4>(q, w.nchunk, s) : launch_wgrad_tc_raw_nx<false, 8>(q, w.nchunk, s);
+        return true;
+    }
     *err = split ? launch_wgrad_tc_t<true>(q, w.nchunk, s) : launch_wgrad_tc_t<false>(q, w.nchunk, s);
     return true;
 }

@@ -55,6 +55,7 @@ SIGNATURES = {
     "crk_set_precision": (i32, [i32]),
     "crk_get_precision": (i32, []),
     "crk_debug_tc_disable": (i32, [i32]),
+    "crk_debug_opt_disable": (i32, [i32]),
     "crk_debug_timestamps": (i32, [vp, i32, i32]),
     "crk_launch_count": (C.c_ulonglong, []),
     "crk_timing_enable": (i32, [i32]),
@@ -121,6 +122,8 @@ def lib():
         if mode not in PRECISIONS:
             raise RuntimeError(f"CRANK_B200_PRECISION={mode!r}: expected one of {sorted(PRECISIONS)}")
         handle.crk_set_precision(PRECISIONS[mode])
+        # A/B switch for optional optimisations (see crk_debug_opt_disable in include/crank_b200.h)
+        handle.crk_debug_opt_disable(int(os.environ.get("CRANK_B200_OPT_DISABLE", "0")))
     return _lib
 
 

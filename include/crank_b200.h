@@ -42,6 +42,11 @@ int crk_get_precision(void);
 /* debugging: force tensor-core kernel families back to the fp32 kernels
  * (bit 1 fused forward, 2 conv/dgrad, 4 wgrad, 8 gate backward) */
 int crk_debug_tc_disable(int mask);
+/* debugging / A-B measurement: switch optional optimisations off (results are unchanged up to the
+ * summation order of bias gradients): bit 1 programmatic dependent launch, 2 bias column sums fused into
+ * the tensor-core wgrad kernel, 4 128-bit epilogue of the tensor-core conv kernel, 8 shared-memory raw tile
+ * feeding the k taps of the tensor-core wgrad kernel (off: one global fetch per tap) */
+int crk_debug_opt_disable(int mask);
 
 /* instrumentation: number of kernels the library has launched in this process; optional CUDA-event
  * timing of one kernel family (ids: 1 resblock_fwd, 2 wgrad, 3 conv, 4 resblock_bwd_gate, 5 vq_argmin;

@@ -81,3 +81,47 @@ def test_quantiser_properties_at_full_size():
     # EMA statistics: counts sum to the number of frames (ema_size was 0 before the first update)
     n = q.ema_size.sum().item()
     assert abs(n - 0.01 * 64 * 500) / (0.01 * 64 * 500) < 1e-4
+
+
+def test_optional_optimisations_do_not_change_results_at_full_size():
+    """Programmatic dependent launch, the 128-bit conv epilogue, the shared-memory raw tile of the wgrad
+    taps and the bias column sums fused into the tensor-core wgrad kernel are pure scheduling / data-path
+    changes: with all of them switched off (crk_debug_opt_disable(15)) every output must be bit-identical,
+    except the bias gradients, whose summation ORDER differs (fused: per-thread running sums, then a
+    fixed-order combine)."""
+    from crank_b200 import lib as L
+    from crank_b200.parallel_wavegan.models import ParallelWaveGANGenerator
+
+    torch.manual_seed(0)
+    B, T = 64, 500
+    net = ParallelWaveGANGenerator(in_channels=128, out_channels=80, kernel_size=5, layers=8, stacks=4,
+                                   aux_channels=34, upsample_conditional_features=False).cuda()
+    x = torch.randn(B, T, 128, device="cuda")
+    c = torch.randn(B, T, 34, device="cuda")
+    dy = torch.randn(B, T, 80, device="cuda")
+    is_bias = torch.zeros_like(net.theta, dtype=torch.bool)
+    for d in net._descs:
+        if d.b_off >= 0:
+            is_bias[d.b_off : d.b_off + d.cout] = True
+    res = {}
+    try:
+        for mask in (15, 0, 0):       # off, on, on again (run-to-run determinism with PDL on)
+            L.check(L.lib().crk_debug_opt_disable(mask), "opt mask")
+            xi = x.clone().requires_grad_(True)
+            ci = c.clone().requires_grad_(True)
+            net.zero_grad(set_to_none=True)
+            y = net.forward_cl(xi, ci)
+            y.backward(dy)
+            torch.cuda.synchronize()
+            res.setdefault(mask, []).append((y.detach().clone(), xi.grad.clone(), ci.grad.clone(), net.theta.grad.clone()))
+    finally:
+        L.lib().crk_debug_opt_disable(0)
+    off, on, on2 = res[15][0], res[0][0], res[0][1]
+    for a, b_ in zip(on, on2):
+        assert torch.equal(a, b_), "two runs with the optimisations on differ"
+    for n, a, b_ in zip(("y", "dx", "dc"), off[:3], on[:3]):
+        assert not torch.isnan(b_).any()
+        assert torch.equal(a, b_), f"{n} changed with the optimisations on"
+    assert torch.equal(off[3][~is_bias], on[3][~is_bias]), "weight gradients changed"
+    gb_off, gb_on = off[3][is_bias], on[3][is_bias]
+    assert ((gb_off - gb_on).abs().max() / gb_off.abs().max()).item() < 1e-5
