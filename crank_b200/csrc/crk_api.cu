@@ -365,12 +365,12 @@ int crk_stft_loss_fwd(const float* x, int ldx, const float* y, int ldy, int B, i
     return CRK_OK;
 }
 int crk_stft_loss_bwd(const float* x, int ldx, const float* y, int ldy, int B, int T, int D,
-                      int n_fft, int hop, int win, const float* g, float scale, float* dx, int lddx,
-                      int accumulate, void* stream) {
+                      int n_fft, int hop, int win, const float* g, const float* glog, float scale, float* dx,
+                      int lddx, int accumulate, void* stream) {
     StftParams p;
     int rc = stft_params(&p, x, ldx, y, ldy, B, T, D, n_fft, hop, win);
     if (rc) return rc;
-    if (!g || !dx) return CRK_ERR_ARG;
+    if ((!g && !glog) || !dx) return CRK_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     if (!accumulate) {
         const long long rows = (long long)B * T;
@@ -381,7 +381,7 @@ int crk_stft_loss_bwd(const float* x, int ldx, const float* y, int ldy, int B, i
     long long nblk = cdivl(nfr, 8);
     if (nblk > 148 * 8) nblk = 148 * 8;
     const size_t smem = (size_t)(3 * n_fft + 16 * p.bins) * sizeof(float);
-    k_stft_loss_bwd<<<(unsigned)nblk, CRK_THREADS, smem, s>>>(p, g, scale, dx, lddx);
+    k_stft_loss_bwd<<<(unsigned)nblk, CRK_THREADS, smem, s>>>(p, g, glog, scale, dx, lddx);
     API_TRY(launch_check());
     return CRK_OK;
 }

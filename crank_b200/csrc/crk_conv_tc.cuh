@@ -21,6 +21,7 @@ struct ConvTcParams {
     int Kpad, Npad;       // K rounded up to 8, UMMA N (multiple of 16, <= 128)
     int dbg;
     int vec_epi;          // epilogue may use 128-bit accesses (Cout, row strides and pointers all 16 B aligned)
+    int opt_stage;        // A tile staged in one deep batch of loads
     // gate-backward mode (gate != 0), the tensor-core version of k_resblock_bwd_gate:
     //   A[row][4q+r] = r<2 ? sqrt(.5)*dH[row][2q+r] : dS[row][2q+r-2]  (also written to GOS),  acc = A . Wos^T = dz
     //   epilogue: dg = gate'(dz; ta, sb) -> DG (interleaved gate order),  z = ta*sb -> Z
@@ -30,10 +31,9 @@ struct ConvTcParams {
 };
 
 // A-tile staging of the gate-backward mode: 128 rows x 128 interleaved [sqrt(.5)*dH | dS] columns
-template <bool SPLIT>
+template <bool SPLIT, int U>
 __device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats, const ConvTcParams& q, int b, int t0) {
     const ConvParams& p = q.p;
-    constexpr int U = 4;
     const int total = CRK_TC_TM * 32;                      // (row, pair q): one float4 of A each
     for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
         float2 h[U], sg[U];
@@ -71,7 +71,7 @@ __device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats
     }
 }
 
-template <bool SPLIT, int U>
+template <bool SPLIT, int U, bool HASMUL>
 __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_floats, const ConvParams& p, int Kpad,
                                                  int b, int tstart, int rows) {
     const int c4n = Kpad >> 2;
@@ -81,13 +81,14 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
     // U independent float4 loads per thread per round: with one CTA (8 warps) per SM every global round
     // trip costs ~2-3K cycles (measured), so the whole tile should be in flight at once when it fits
     for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
-        float4 v[U], m[U];
+        float4 v[U], m[HASMUL ? U : 1];
         int off[U];
+        if (!HASMUL) m[0] = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int idx = base + u * blockDim.x;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (HASMUL) m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
             off[u] = -1;
             if (idx < total) {
                 const int r = idx / c4n, c4 = idx - r * c4n;
@@ -98,14 +99,14 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
                     const size_t row = (size_t)b * p.T + tt;
                     if (vec) {
                         v[u] = __ldg(reinterpret_cast<const float4*>(p.X + row * p.ldx) + c4);
-                        if (p.xmul) m[u] = __ldg(reinterpret_cast<const float4*>(p.xmul + row * p.ldxmul) + c4);
+                        if (HASMUL) m[u] = __ldg(reinterpret_cast<const float4*>(p.xmul + row * p.ldxmul) + c4);
                     } else {
                         const float* sp = p.X + row * p.ldx + c;
                         v[u].x = __ldg(sp);
                         v[u].y = c + 1 < p.Cin ? __ldg(sp + 1) : 0.f;
                         v[u].z = c + 2 < p.Cin ? __ldg(sp + 2) : 0.f;
                         v[u].w = c + 3 < p.Cin ? __ldg(sp + 3) : 0.f;
-                        if (p.xmul) {
+                        if (HASMUL) {
                             const float* ms = p.xmul + row * p.ldxmul + c;
                             m[u].x = __ldg(ms);
                             m[u].y = c + 1 < p.Cin ? __ldg(ms + 1) : 0.f;
@@ -119,11 +120,12 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (off[u] < 0) continue;
+            const float4 mm = m[HASMUL ? u : 0];
             float4 x;
-            x.x = apply_act(v[u].x * p.pro_scale, p.pro_act, p.pro_slope) * m[u].x;
-            x.y = apply_act(v[u].y * p.pro_scale, p.pro_act, p.pro_slope) * m[u].y;
-            x.z = apply_act(v[u].z * p.pro_scale, p.pro_act, p.pro_slope) * m[u].z;
-            x.w = apply_act(v[u].w * p.pro_scale, p.pro_act, p.pro_slope) * m[u].w;
+            x.x = apply_act(v[u].x * p.pro_scale, p.pro_act, p.pro_slope) * mm.x;
+            x.y = apply_act(v[u].y * p.pro_scale, p.pro_act, p.pro_slope) * mm.y;
+            x.z = apply_act(v[u].z * p.pro_scale, p.pro_act, p.pro_slope) * mm.z;
+            x.w = apply_act(v[u].w * p.pro_scale, p.pro_act, p.pro_slope) * mm.w;
             if (SPLIT) {
                 float4 h, l;
                 tc::split_tf32(x.x, h.x, l.x); tc::split_tf32(x.y, h.y, l.y);
@@ -195,8 +197,13 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
         for (int st = 0; st < 2 && st < nsteps; ++st) produce(st);
     // (deeper batches were measured: no gain in the 3xTF32 mode, and the extra registers cost the plain
     //  TF32 variant its second resident CTA per SM, which matters far more)
-    if (q.gate) tc_stage_gos<SPLIT>(Xh, Xl, csx, q, b, t0);
-    else tc_stage_act_pro<SPLIT, 4>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
+    // the whole A tile in ONE batch of independent loads when the registers allow (3xTF32 variant: one CTA
+    // per SM, 255 registers): a batch costs ~2.4K cycles however many loads it holds (measured: 5 batches
+    // of 4 = 12K cycles for the K=128 dgrad tile)
+    if (q.gate) tc_stage_gos<SPLIT, (SPLIT ? 16 : 4)>(Xh, Xl, csx, q, b, t0);
+    else if (p.xmul) tc_stage_act_pro<SPLIT, 4, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
+    else if (q.opt_stage) tc_stage_act_pro<SPLIT, (SPLIT ? 18 : 6), false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
+    else tc_stage_act_pro<SPLIT, 4, false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
     tc::fence_proxy_async_smem();
     __syncthreads();
     dbg_stamp(q.dbg, 1);
@@ -204,22 +211,30 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     // one elected lane per role; the other 31 lanes of that warp park at __syncwarp (no spinning next to
     // the working lane)
     if (warp == 0) {
-        if (lane == 0)
+        if (lane == 0) {
+            long long wfree = 0;
             for (int st = 2; st < nsteps; ++st) {
+                const long long c0 = q.dbg ? clock64() : 0;
                 ok &= tc::mbar_wait(&bar_free[st & 1], ((st - 2) >> 1) & 1);
+                if (q.dbg) wfree += clock64() - c0;
                 produce(st);
             }
+            dbg_put(q.dbg, 9, wfree);
+        }
         __syncwarp();
     } else if (warp == 1) {
       if (lane == 0) {
         const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
         const uint32_t xh_s = tc::smem_u32(Xh), xl_s = tc::smem_u32(Xl);
         uint32_t acc = 0;
+        long long wfull = 0;
         for (int st = 0; st < nsteps; ++st) {
             const int j = st / nseg, sg = st - j * nseg;
             const int ch0 = sg * 16;
             const int nch = (kch - ch0) < 16 ? (kch - ch0) : 16;
+            const long long c0 = q.dbg ? clock64() : 0;
             ok &= tc::mbar_wait(&bar_full[st & 1], (st >> 1) & 1);
+            if (q.dbg) wfull += clock64() - c0;
             tc::tc_fence_after();
             tc_issue_kmajor<SPLIT>(tmem, xh_s + ch0 * csx * 4, xl_s + ch0 * csx * 4, csx * 4, j * p.dil,
                                    tc::smem_u32(slot_hi[st & 1]), tc::smem_u32(slot_lo[st & 1]), csw * 4,
@@ -227,6 +242,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
             tc::umma_commit(&bar_free[st & 1]);
         }
         tc::umma_commit(&bar_acc);
+        dbg_put(q.dbg, 8, wfull);
       }
       __syncwarp();
     }
@@ -417,6 +433,7 @@ inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc,
         ConvTcParams q;
         q.p = p; q.Wtc = wtc; q.Kpad = kpad; q.Npad = npad; q.dbg = 0; q.gate = 0;
         auto al = [](const float* ptr, int ld) { return ptr == nullptr || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)); };
+        q.opt_stage = !(opt_disable_mask() & 16);
         q.vec_epi = !(opt_disable_mask() & 4) && (p.Cout & 3) == 0 && p.Y != nullptr && al(p.Y, p.ldy) && al(p.mul_src, p.ldmul) &&
                     al(p.R, p.ldr) && al(p.dact_src, p.lddact);
         q.g_dH = q.g_dS = q.g_TaSb = nullptr; q.g_DG = q.g_GOS = q.g_Z = nullptr;
@@ -433,7 +450,7 @@ inline bool gate_bwd_tc(const ResBwdGateParams& g, const float* wos_tct, cudaStr
     ConvTcParams q;
     q.p = conv_params_default();
     q.p.B = g.B; q.p.T = g.T; q.p.Cin = 128; q.p.Cout = 64; q.p.k = 1; q.p.dil = 1; q.p.padl = 0;
-    q.Wtc = wos_tct; q.Kpad = 128; q.Npad = 64; q.dbg = 0; q.gate = 1; q.vec_epi = 0;
+    q.Wtc = wos_tct; q.Kpad = 128; q.Npad = 64; q.dbg = 0; q.gate = 1; q.vec_epi = 0; q.opt_stage = 0;
     q.g_dH = g.dH; q.g_dS = g.dS; q.g_TaSb = g.TaSb; q.g_DG = g.DG; q.g_GOS = g.GOS; q.g_Z = g.Z;
     const bool split = mode == CRK_PREC_TF32X3;
     if (conv_tc_smem(q, split) > 220 * 1024) return false;

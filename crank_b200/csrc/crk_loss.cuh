@@ -230,7 +230,10 @@ __global__ void k_zero_panel(float* dx, int ld, int D, long long rows) {
 
 // one warp per (b, d, m) frame: lanes over bins build the per-bin coefficient, then lanes over
 // window samples scatter-add into dx (atomics: frames may overlap / reflect onto the same sample).
+// g / glog: upstream gradients of the magnitude and the log-magnitude means (either may be null):
+//   d|mx - my|/dre = sgn * re/mx,   d|log mx - log my|/dre = sgn * re/mx^2   (same sign: log is monotonic)
 __global__ void __launch_bounds__(CRK_THREADS) k_stft_loss_bwd(const StftParams p, const float* __restrict__ g,
+                                                               const float* __restrict__ glog,
                                                                float scale, float* __restrict__ dx, int lddx) {
     extern __shared__ float4 crk_smem4[];
     float* ct = reinterpret_cast<float*>(crk_smem4);
@@ -242,7 +245,9 @@ __global__ void __launch_bounds__(CRK_THREADS) k_stft_loss_bwd(const StftParams 
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long nfr = (long long)p.B * p.D * p.M;
-    const float gg = g[0] * scale / (float)((long long)p.B * p.D * p.M * p.bins);
+    const float inv_n = scale / (float)((long long)p.B * p.D * p.M * p.bins);
+    const float gg = g ? g[0] * inv_n : 0.f;
+    const float gl = glog ? glog[0] * inv_n : 0.f;
     const int woff = (p.n_fft - p.win) / 2;
     for (long long fr = (long long)blockIdx.x * 8 + w; fr < nfr; fr += (long long)gridDim.x * 8) {
         const int d = (int)(fr % p.D);
@@ -259,7 +264,9 @@ __global__ void __launch_bounds__(CRK_THREADS) k_stft_loss_bwd(const StftParams 
             float coef = 0.f;
             if (px >= 1e-7f) {
                 const float df = mx - my;
-                coef = gg * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f)) / mx;
+                const float sgn = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+                coef = sgn * (gg / mx);
+                if (glog) coef += sgn * (gl / (mx * mx));
             }
             cre[w * p.bins + bin] = coef * rx;
             cim[w * p.bins + bin] = coef * ix;

@@ -204,8 +204,11 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
         // ===== MMA issuer: conv taps =====
         const uint32_t xh_s = tc::smem_u32(Xh), xl_s = tc::smem_u32(Xl);
         uint32_t acc = 0;
+        long long wfull = 0;
         for (int j = 0; j < p.k; ++j) {
+            const long long c0 = q.dbg ? clock64() : 0;
             ok &= tc::mbar_wait(&bar_full[j & 1], (j >> 1) & 1);
+            if (q.dbg) wfull += clock64() - c0;
             tc::tc_fence_after();
             tc_issue_kmajor<SPLIT>(tmem, xh_s, xl_s, csx * 4, j * p.dil, tc::smem_u32(slot_hi[j & 1]),
                                    tc::smem_u32(slot_lo[j & 1]), CSW * 4, 64, idesc, acc);
@@ -213,6 +216,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
         }
         tc::umma_commit(&bar_acc[0]);
         if (!has_aux) tc::umma_commit(&bar_acc[1]);
+        dbg_put(q.dbg, 8, wfull);
       }
       __syncwarp();
     }

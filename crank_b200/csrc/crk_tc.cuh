@@ -22,6 +22,11 @@ __device__ long long* g_crk_dbg = nullptr;
 __device__ __forceinline__ void dbg_stamp(int enabled, int slot) {
     if (enabled && g_crk_dbg && threadIdx.x == 64) g_crk_dbg[(size_t)blockIdx.x * 16 + slot] = clock64();
 }
+// single-thread diagnostic accumulators (slots 8..15 of the CTA's stamp row): e.g. cycles an MMA issuer
+// spent waiting for weight bytes, or a TMA producer for a free ring slot
+__device__ __forceinline__ void dbg_put(int enabled, int slot, long long v) {
+    if (enabled && g_crk_dbg) g_crk_dbg[(size_t)blockIdx.x * 16 + slot] = v;
+}
 // host side: which launch of which kernel family records stamps
 struct DbgSel { int kind = 0; int target = 0; int count = 0; };
 inline DbgSel& dbg_sel() { static DbgSel d; return d; }

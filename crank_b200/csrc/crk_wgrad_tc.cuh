@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
         wg_load_raw<NR>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
     };
 
+    long long dbg_acc[3] = {0, 0, 0};                      // thread 64: slot waits / transposition / barrier
     if (tile_beg < tile_end) load_tile(tile_beg);
     for (int tile = tile_beg; tile < tile_end; ++tile) {
         if (tile == tile_beg) dbg_stamp(q.dbg, 0);
@@ -450,13 +451,18 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
         if (tile == tile_beg) dbg_stamp(q.dbg, 2);
         for (int j = 0; j < p.k; ++j, ++step) {
             const int sl = step % NS;
+            const bool dbg64 = q.dbg && threadIdx.x == 64;
+            const long long c0 = dbg64 ? clock64() : 0;
             // the MMAs of step - NS (this tile; earlier tiles are covered by bar_tile) read this slot
             if (j >= NS) ok &= tc::mbar_wait(&bar_slot[sl], ((step - NS) / NS) & 1);
+            const long long c1 = dbg64 ? clock64() : 0;
             wg_transpose_raw<SPLIT, NX>(xraw, rstride, slot_hi(sl), slot_lo(sl), csx, q.Npad, j * p.dil);
             tc::fence_proxy_async_smem();
             tc::tc_fence_before();
+            const long long c2 = dbg64 ? clock64() : 0;
             __syncthreads();
             tc::tc_fence_after();
+            if (dbg64) { dbg_acc[0] += c1 - c0; dbg_acc[1] += c2 - c1; dbg_acc[2] += clock64() - c2; }
             if (threadIdx.x == 32) {
                 uint32_t acc = ntile_done > 0 ? 1u : 0u;
                 tc_issue_kmajor<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi(sl)),
@@ -474,6 +480,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     if (!ok) timeout_s = 1;
     __syncthreads();
     dbg_stamp(q.dbg, 5);
+    if (q.dbg && threadIdx.x == 64) { dbg_put(1, 8, dbg_acc[0]); dbg_put(1, 9, dbg_acc[1]); dbg_put(1, 10, dbg_acc[2]); }
 
     // ---- epilogue (identical to k_wgrad_tc) ----
     const int co = (warp & 3) * 32 + lane;

@@ -88,7 +88,7 @@ SIGNATURES = {
     "crk_masked_loss_bwd": (i32, [vp, i32, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     "crk_stft_loss_ws_floats": (i64, [i32, i32, i32, i32, i32]),
     "crk_stft_loss_fwd": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
-    "crk_stft_loss_bwd": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, f32, vp, i32, i32, vp]),
+    "crk_stft_loss_bwd": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, i32, i32, vp]),
     "crk_ce_ws_floats": (i64, [i64]),
     "crk_ce_fwd": (i32, [vp, i32, vp, i64, i32, i64, vp, vp, vp]),
     "crk_ce_bwd": (i32, [vp, i32, vp, i64, i32, i64, vp, vp, vp, i32, vp]),

@@ -54,9 +54,8 @@ class STFTLoss(nn.Module):
         """x, y (B, T, D): L1 between STFT magnitudes of every feature-dimension trajectory."""
         mag, lmag = ops.StftLossFn.apply(x, y, int(self.fft_size), int(self.hop_size), int(self.win_size))
         if self.logratio == 0:
-            return mag
-        # TODO(round 2): the log-magnitude term has a forward value but no gradient kernel yet
-        raise NotImplementedError("logratio != 0 is not supported (all recipes use logratio 0)")
+            return mag                     # == (1 - 0) * mag + 0 * lmag exactly; skips the log-term backward
+        return (1 - self.logratio) * mag + self.logratio * lmag
 
 
 class MultiSizeSTFTLoss(nn.Module):

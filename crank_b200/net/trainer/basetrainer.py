@@ -150,7 +150,7 @@ class BaseTrainer(object):
         values = self._get_loss_dict()
         keys = [k for k, v in loss.items() if isinstance(v, torch.Tensor)]
         if keys:
-            packed = torch.stack([loss[k].detach().reshape(()).float() for k in keys]).tolist()
+            packed = _dp.average_loss_vector(torch.stack([loss[k].detach().reshape(()).float() for k in keys])).tolist()
             for k, v in zip(keys, packed):
                 values[k] = values.get(k, 0.0) + v
         for k in loss:

@@ -10,6 +10,7 @@ scalar (no ones_like / masked_select tensors, trainer_lsgan.py:154-171).
 import torch
 
 from ... import ops
+from .. import _dp
 from .trainer_vqvae import VQVAETrainer
 
 
@@ -31,6 +32,7 @@ class LSGANTrainer(VQVAETrainer):
         self._check_gan_start()
 
     def train(self, batch, phase="train"):
+        _dp.begin_step(batch)
         loss = self._get_loss_dict()
         if self.gan_flag:
             loss = self.forward_lsgan(batch, loss, phase=phase)

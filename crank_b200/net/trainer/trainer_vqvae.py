@@ -10,6 +10,7 @@ their host syncs while computing the same means.
 import torch
 
 from ... import ops
+from .. import _dp
 from .basetrainer import BaseTrainer, pick_cv_speakers
 
 
@@ -27,6 +28,7 @@ class VQVAETrainer(BaseTrainer):
 
     # ---- public steps --------------------------------------------------------------------------
     def train(self, batch, phase="train"):
+        _dp.begin_step(batch)
         loss = self._get_loss_dict()
         if self.cycle_flag:
             loss = self.forward_cycle(batch, loss, phase=phase)

@@ -224,10 +224,12 @@ class MaskedLossFn(torch.autograd.Function):
         if m is not None:
             saved.append(m)
         ctx.save_for_backward(*saved)
-        return out[0], out[1]
+        cnt = out[2]
+        ctx.mark_non_differentiable(cnt)
+        return out[0], out[1], cnt
 
     @staticmethod
-    def backward(ctx, g1, g2):
+    def backward(ctx, g1, g2, _gcnt):
         saved = list(ctx.saved_tensors)
         x, out = saved[:2]
         rest = saved[2:]
@@ -244,8 +246,25 @@ class MaskedLossFn(torch.autograd.Function):
         return dx, None, None, None
 
 
+# Data-parallel exactness hook (set by crank_b200.net._dp.enable): a masked mean computed on this rank
+# over `count` selected elements becomes this rank's share of the GLOBAL mean  sum_r(num_r) / sum_r(count_r)
+# when it is multiplied by  world * count / sum_r(count_r)  (the gradient all-reduce then divides by world).
+#   hook(key_tensor, shift, count) -> 0-dim weight tensor, or None when the weight is exactly 1
+_mean_weight_hook = None
+
+
+def set_mean_weight_hook(fn):
+    global _mean_weight_hook
+    _mean_weight_hook = fn
+
+
 def masked_l1_mse(x, y, mask=None, shift=0):
-    return MaskedLossFn.apply(x, y, mask, shift)
+    l1, mse, cnt = MaskedLossFn.apply(x, y, mask, shift)
+    if _mean_weight_hook is not None and mask is not None:
+        w = _mean_weight_hook(mask, int(shift), cnt)
+        if w is not None:
+            return l1 * w, mse * w
+    return l1, mse
 
 
 class StftLossFn(torch.autograd.Function):
@@ -262,17 +281,20 @@ class StftLossFn(torch.autograd.Function):
                L.ptr(out), L.ptr(ws))
         ctx.meta = (B, T, D, ldx, ldy, n_fft, hop, win)
         ctx.save_for_backward(x, y)
-        o0, o1 = out[0], out[1]
-        ctx.mark_non_differentiable(o1)
-        return o0, o1
+        ctx.set_materialize_grads(False)      # an unused output's gradient arrives as None, not zeros
+        return out[0], out[1]
 
     @staticmethod
-    def backward(ctx, g, _glog):
+    def backward(ctx, g, glog):
         x, y = ctx.saved_tensors
         B, T, D, ldx, ldy, n_fft, hop, win = ctx.meta
         dx = torch.empty(B, T, D, dtype=_f32, device=x.device)
+        g = g.contiguous() if g is not None else None
+        glog = glog.contiguous() if glog is not None else None
+        if g is None and glog is None:
+            return torch.zeros_like(dx), None, None, None, None
         L.call("crk_stft_loss_bwd", L.ptr(x), ldx, L.ptr(y), ldy, B, T, D, n_fft, hop, win,
-               L.ptr(g.contiguous()), C.c_float(1.0), L.ptr(dx), D, 0)
+               L.ptr(g), L.ptr(glog), C.c_float(1.0), L.ptr(dx), D, 0)
         return dx, None, None, None, None
 
 
@@ -292,10 +314,12 @@ class CrossEntropyFn(torch.autograd.Function):
                int(ignore_index), L.ptr(out), L.ptr(ws))
         ctx.meta = (Fn, S, int(ignore_index))
         ctx.save_for_backward(logits, labels, out)
-        return out[0]
+        cnt = out[1]
+        ctx.mark_non_differentiable(cnt)
+        return out[0], cnt
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _gcnt):
         logits, labels, out = ctx.saved_tensors
         Fn, S, ign = ctx.meta
         dl = torch.empty(Fn, S, dtype=_f32, device=logits.device)
@@ -305,7 +329,12 @@ class CrossEntropyFn(torch.autograd.Function):
 
 
 def cross_entropy(logits, labels, ignore_index=-100):
-    return CrossEntropyFn.apply(logits, labels, ignore_index)
+    ce, cnt = CrossEntropyFn.apply(logits, labels, ignore_index)
+    if _mean_weight_hook is not None:
+        w = _mean_weight_hook(labels, 0, cnt)
+        if w is not None:
+            return ce * w
+    return ce
 
 
 # ---------------------------------------------------------------------------------------------

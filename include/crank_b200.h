@@ -45,7 +45,8 @@ int crk_debug_tc_disable(int mask);
 /* debugging / A-B measurement: switch optional optimisations off (results are unchanged up to the
  * summation order of bias gradients): bit 1 programmatic dependent launch, 2 bias column sums fused into
  * the tensor-core wgrad kernel, 4 128-bit epilogue of the tensor-core conv kernel, 8 shared-memory raw tile
- * feeding the k taps of the tensor-core wgrad kernel (off: one global fetch per tap) */
+ * feeding the k taps of the tensor-core wgrad kernel (off: one global fetch per tap), 16 single-batch staging
+ * of the tensor-core conv kernel's activation tile */
 int crk_debug_opt_disable(int mask);
 
 /* instrumentation: number of kernels the library has launched in this process; optional CUDA-event
@@ -199,14 +200,16 @@ int crk_masked_loss_bwd(const float* x, int ldx, const float* y, int ldy, float 
 
 /* STFT-magnitude trajectory L1 (crank/net/module/loss.py:50-85): each feature dimension's time
  * trajectory -> STFT(n_fft, hop, hann(win) centred in n_fft, center=True reflect) ->
- * sqrt(clamp(re^2+im^2, 1e-7)) -> mean |mag_x - mag_y|.   out[0] = loss. */
+ * sqrt(clamp(re^2+im^2, 1e-7)) -> out[0] = mean |mag_x - mag_y|, out[1] = mean |log mag_x - log mag_y|
+ * (STFTLoss.forward combines them as (1 - logratio) * out[0] + logratio * out[1], loss.py:80-84). */
 long long crk_stft_loss_ws_floats(int B, int T, int D, int n_fft, int hop);
 int crk_stft_loss_fwd(const float* x, int ldx, const float* y, int ldy, int B, int T, int D,
                       int n_fft, int hop, int win, float* out, float* ws, void* stream);
-/* dx (+)= g[0] * scale * dLoss/dx   (accumulate != 0 adds into dx) */
+/* dx (+)= scale * (g[0] * d out[0]/dx + glog[0] * d out[1]/dx); g or glog may be NULL (term absent);
+ * accumulate != 0 adds into dx */
 int crk_stft_loss_bwd(const float* x, int ldx, const float* y, int ldy, int B, int T, int D,
-                      int n_fft, int hop, int win, const float* g, float scale, float* dx, int lddx,
-                      int accumulate, void* stream);
+                      int n_fft, int hop, int win, const float* g, const float* glog, float scale, float* dx,
+                      int lddx, int accumulate, void* stream);
 
 /* cross entropy with ignore_index (torch.nn.CrossEntropyLoss(ignore_index=-100),
  * crank/net/trainer/utils.py:26).  logits (F,S) ld ldl, S<=64; out[0]=loss, out[1]=#valid rows */

@@ -32,8 +32,13 @@ for name, (kid, idx, labels, n) in sel.items():
     L.check(L.lib().crk_debug_timestamps(buf.data_ptr(), kid, idx))
     run()
     L.check(L.lib().crk_debug_timestamps(None, 0, 0))
-    t = buf.view(-1, 16)[:, :n].double().cpu()
-    t = t[t[:, 0] > 0]
+    full = buf.view(-1, 16).double().cpu()
+    full = full[full[:, 0] > 0]
+    t = full[:, :n]
     d = (t[:, 1:] - t[:, :-1]).mean(0)
+    diag = {"resblock_fwd k5 d2": ["issuer wait for weights"],
+            "conv dgrad k5 (K128,N64)": ["issuer wait for weights", "producer wait for free slot"],
+            "wgrad conv k5": ["slot waits", "transposition", "barrier"]}[name]
+    print("   diag (cycles, CTA mean):", {l: int(full[:, 8 + i].mean()) for i, l in enumerate(diag)})
     print(prec, name, "CTAs", len(t), {l: int(v) for l, v in zip(labels, d)}, "total", int((t[:, n - 1] - t[:, 0]).mean()),
           "kernel span", int(t[:, n - 1].max() - t[:, 0].min()))

@@ -45,3 +45,75 @@ def test_dp_gradient_bucket_and_stats_reduce_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)], res
+
+
+def _ragged_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from crank_b200 import ops
+    from crank_b200.net import _dp
+
+    _dp.enable()
+    assert ops._mean_weight_hook is _dp.mean_weight
+    # big batch = 4 utterances x 6 frames with ragged lengths; rank r owns utterances [2r, 2r+1]
+    g = torch.Generator().manual_seed(0)
+    B, T, D = 4, 6, 3
+    x = torch.randn(B, T, D, generator=g)
+    y = torch.randn(B, T, D, generator=g)
+    flen = torch.tensor([6, 2, 3, 5])
+    mask = (torch.arange(T)[None, :] < flen[:, None]).unsqueeze(-1)               # (B, T, 1) bool
+    labels = torch.where(mask.squeeze(-1), torch.randint(0, 4, (B, T), generator=g), torch.tensor(-100))
+    theta = torch.nn.Parameter(torch.tensor([0.7, -1.3, 0.4]))
+
+    def masked_mse(xx, yy, mm, th):
+        d = (xx * th - yy) ** 2
+        sel = mm.expand_as(d)
+        return (d * sel).sum() / sel.sum(), sel.sum()
+
+    # reference: one device, the whole batch
+    ref, _ = masked_mse(x, y, mask, theta)
+    (gref,) = torch.autograd.grad(ref, theta)
+    # this rank's share
+    sl = slice(2 * rank, 2 * rank + 2)
+    batch = {"decoder_mask": mask[sl].contiguous(), "org_h": labels[sl].contiguous()}
+    _dp.begin_step(batch)
+    local, cnt = masked_mse(x[sl], y[sl], batch["decoder_mask"], theta)
+    w = _dp.mean_weight(batch["decoder_mask"], 0, cnt)
+    loss = local * w
+    theta.grad = torch.autograd.grad(loss, theta)[0]
+    _dp.average_gradients([theta])
+    ok = torch.allclose(theta.grad, gref, rtol=1e-6, atol=1e-7)
+    rep = _dp.average_loss_vector(torch.stack([loss.detach()]))
+    ok = ok and torch.allclose(rep[0], ref.detach(), rtol=1e-6)
+    # label tensor (cross-entropy ignore_index counts) served from the same per-step all-reduce
+    n_valid = (batch["org_h"] != -100).sum()
+    wl = _dp.mean_weight(batch["org_h"].reshape(-1), 0, n_valid)
+    ok = ok and abs(float(wl) - world * float(n_valid) / float((labels != -100).sum())) < 1e-6
+    # a tensor that is not part of the batch: reduced on the fly
+    other = torch.ones(3)
+    wo = _dp.mean_weight(other, 0, torch.tensor(float(rank + 1)))
+    ok = ok and abs(float(wo) - world * (rank + 1) / 3.0) < 1e-6
+    # equal counts -> weight exactly 1 (bit-identical to the single-device step)
+    eq = {"encoder_mask": torch.ones(2, T, 1, dtype=torch.bool)}
+    _dp.begin_step(eq)
+    ok = ok and float(_dp.mean_weight(eq["encoder_mask"], 0, torch.tensor(12.0))) == 1.0
+    _dp.disable()
+    ok = ok and ops._mean_weight_hook is None and _dp.mean_weight(other, 0, torch.tensor(1.0)) is None
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_dp_ragged_masked_means_match_big_batch_world2():
+    """with ragged masks the big-batch mean is sum(num)/sum(count); weighting each
+    rank's local mean by world*count_r/sum(count) before the gradient average reproduces it exactly."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_ragged_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)], res

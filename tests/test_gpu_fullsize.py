@@ -17,6 +17,11 @@ def lib_precision():
 
 @pytest.mark.parametrize("B,T", [(64, 500), (8, 4096), (256, 128)])
 def test_tensor_core_and_cuda_core_kernels_agree_at_full_size(lib_precision, B, T):
+    """Forward: the two kernel families on the same inputs.  Backward: ONE forward (tensor cores), then the
+    backward of that very graph run by each family.  Both backwards then read the same saved activations,
+    so the ReLU'(skip-sum) / ReLU'(head) masks are identical and the comparison can be strict (two
+    independent forwards agree to ~1e-6, which still flips ~1 mask per 1e5 pre-activations and changes
+    the gradient of those frames by O(1): that is chaos of the function, not kernel error)."""
     from crank_b200.parallel_wavegan.models import ParallelWaveGANGenerator
 
     torch.manual_seed(0)
@@ -25,34 +30,26 @@ def test_tensor_core_and_cuda_core_kernels_agree_at_full_size(lib_precision, B, 
     x = torch.randn(B, T, 128, device="cuda")
     c = torch.randn(B, T, 34, device="cuda")
     dy = torch.randn(B, T, 80, device="cuda")
-    res = {}
-    for mode in ("fp32", "tf32x3"):
-        lib_precision(mode)
-        xi = x.clone().requires_grad_(True)
-        ci = c.clone().requires_grad_(True)
-        net.zero_grad(set_to_none=True)
-        y = net.forward_cl(xi, ci)
-        y.backward(dy)
-        res[mode] = (y.detach(), xi.grad, ci.grad, net.theta.grad.clone())
-    # Forward outputs must agree to 1e-4.  Gradients go through ReLU'(skip-sum) / ReLU'(head) masks: a
-    # pre-activation within ~1e-5 of zero flips its mask between two implementations that agree to 1e-5
-    # (measured: ~1 per 1e5 values), which changes the gradient of THAT frame by O(1).  So gradients are
-    # compared frame-wise (one flip reaches +-34 frames through the 8 dilated dgrads): all but a few
-    # percent of the frames within 1e-4, and the parameter gradient
-    # (a sum over frames) within 1e-2.
+
     def rel(a, b_):
         return ((a - b_).abs().max() / a.abs().max()).item()
 
-    y_f, dx_f, dc_f, dth_f = res["fp32"]
-    y_t, dx_t, dc_t, dth_t = res["tf32x3"]
-    for t in (y_t, dx_t, dc_t, dth_t):
-        assert not torch.isnan(t).any()
+    with torch.no_grad():
+        lib_precision("fp32")
+        y_f = net.forward_cl(x, c)
+    lib_precision("tf32x3")
+    xi = x.clone().requires_grad_(True)
+    ci = c.clone().requires_grad_(True)
+    y_t = net.forward_cl(xi, ci)
+    assert not torch.isnan(y_t).any()
     assert rel(y_f, y_t) < 1e-4, f"y: fp32 vs 3xTF32 kernels differ by {rel(y_f, y_t):.2e} at B={B}, T={T}"
-    for n, a, b_ in (("dx", dx_f, dx_t), ("dc", dc_f, dc_t)):
-        rowerr = (a - b_).abs().amax(dim=-1) / a.abs().max()
-        frac = (rowerr > 1e-4).float().mean().item()
-        assert frac < 5e-2, f"{n}: {frac:.2%} of frames differ by more than 1e-4 at B={B}, T={T}"
-    assert rel(dth_f, dth_t) < 1e-2, f"dtheta differs by {rel(dth_f, dth_t):.2e}"
+    grads = {}
+    for mode in ("tf32x3", "fp32"):
+        lib_precision(mode)
+        grads[mode] = torch.autograd.grad(y_t, (xi, ci, net.theta), dy, retain_graph=True)
+    for n, a, b_ in zip(("dx", "dc", "dtheta"), grads["fp32"], grads["tf32x3"]):
+        assert not torch.isnan(b_).any()
+        assert rel(a, b_) < 1e-4, f"{n}: fp32 vs 3xTF32 backward differ by {rel(a, b_):.2e} at B={B}, T={T}"
 
 
 def test_quantiser_properties_at_full_size():

@@ -333,6 +333,26 @@ def test_stft_loss_overlapping_frames_kwargs_path():
     assert_close(xp.grad, xo.grad, 1e-4, "stft loss grad (overlap)")
 
 
+@pytest.mark.parametrize("logratio", [0.3, 1.0])
+def test_stft_loss_logratio_forward_and_gradient(logratio):
+    """(1 - r) * L1(mag) + r * L1(log mag)  (crank/net/module/loss.py:80-84), value and gradient."""
+    from crank_b200.net.module.loss import STFTLoss
+    from oracle.crank_port import stft_mag
+
+    g = torch.Generator().manual_seed(29)
+    x = torch.randn(2, 150, 12, generator=g)
+    y = torch.randn(2, 150, 12, generator=g)
+    xo = x.clone().requires_grad_(True)
+    xm, ym = stft_mag(xo, 32, 10, 20), stft_mag(y, 32, 10, 20)
+    lo = (1 - logratio) * torch.nn.functional.l1_loss(xm, ym) + logratio * torch.nn.functional.l1_loss(xm.log(), ym.log())
+    lo.backward()
+    xp = x.to(_dev()).requires_grad_(True)
+    lp = STFTLoss(fft_size=32, win_size=20, hop_size=10, logratio=logratio)(xp, y.to(_dev()))
+    lp.backward()
+    assert_close(lp, lo, 1e-5, "stft loss (logratio)")
+    assert_close(xp.grad, xo.grad, 1e-4, "stft loss grad (logratio)")
+
+
 def test_cross_entropy_ignore_index():
     from crank_b200 import ops
 
