@@ -71,13 +71,17 @@ __device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats
     }
 }
 
-template <bool SPLIT, int U, bool HASMUL>
+// VECONLY: the host has checked that 128-bit loads are legal (the scalar fallback is compiled out: these
+// kernels execute their straight-line code once per CTA, so every unrolled path that is not taken still
+// costs instruction-cache footprint)
+template <bool SPLIT, int U, bool HASMUL, bool VECONLY>
 __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_floats, const ConvParams& p, int Kpad,
                                                  int b, int tstart, int rows) {
     const int c4n = Kpad >> 2;
     const int total = rows * c4n;
-    const bool vec = ((p.ldx & 3) == 0) && ((p.Cin & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
-                     (p.xmul == nullptr || (((p.ldxmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.xmul) & 15) == 0)));
+    const bool vec = VECONLY ||
+                     (((p.ldx & 3) == 0) && ((p.Cin & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
+                      (p.xmul == nullptr || (((p.ldxmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.xmul) & 15) == 0))));
     // U independent float4 loads per thread per round: with one CTA (8 warps) per SM every global round
     // trip costs ~2-3K cycles (measured), so the whole tile should be in flight at once when it fits
     for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
@@ -97,16 +101,16 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
                 const int c = c4 * 4;
                 if (tt >= 0 && tt < p.T && c < p.Cin) {
                     const size_t row = (size_t)b * p.T + tt;
-                    if (vec) {
+                    if (VECONLY || vec) {
                         v[u] = __ldg(reinterpret_cast<const float4*>(p.X + row * p.ldx) + c4);
-                        if (HASMUL) m[u] = __ldg(reinterpret_cast<const float4*>(p.xmul + row * p.ldxmul) + c4);
-                    } else {
+                        if (HASMUL && p.xmul) m[u] = __ldg(reinterpret_cast<const float4*>(p.xmul + row * p.ldxmul) + c4);
+                    } else if (!VECONLY) {
                         const float* sp = p.X + row * p.ldx + c;
                         v[u].x = __ldg(sp);
                         v[u].y = c + 1 < p.Cin ? __ldg(sp + 1) : 0.f;
                         v[u].z = c + 2 < p.Cin ? __ldg(sp + 2) : 0.f;
                         v[u].w = c + 3 < p.Cin ? __ldg(sp + 3) : 0.f;
-                        if (HASMUL) {
+                        if (HASMUL && p.xmul) {
                             const float* ms = p.xmul + row * p.ldxmul + c;
                             m[u].x = __ldg(ms);
                             m[u].y = c + 1 < p.Cin ? __ldg(ms + 1) : 0.f;
@@ -139,7 +143,13 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
     }
 }
 
-template <bool SPLIT>
+// MODE 0: generic conv / dgrad (every prologue / epilogue option, scalar fallbacks);  MODE 1: gate backward;
+// MODE 2: conv / dgrad whose operands allow 128-bit accesses throughout and have no input multiplier (the
+// hot instances: every dgrad and 1x1 conv of the WaveNet stacks) -- one staging path, one epilogue path.
+#define CRK_CONV_GENERIC 0
+#define CRK_CONV_GATE 1
+#define CRK_CONV_FAST 2
+template <bool SPLIT, int MODE>
 __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcParams q) {
     const ConvParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
@@ -200,10 +210,9 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     // the whole A tile in ONE batch of independent loads when the registers allow (3xTF32 variant: one CTA
     // per SM, 255 registers): a batch costs ~2.4K cycles however many loads it holds (measured: 5 batches
     // of 4 = 12K cycles for the K=128 dgrad tile)
-    if (q.gate) tc_stage_gos<SPLIT, (SPLIT ? 16 : 4)>(Xh, Xl, csx, q, b, t0);
-    else if (p.xmul) tc_stage_act_pro<SPLIT, 4, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
-    else if (q.opt_stage) tc_stage_act_pro<SPLIT, (SPLIT ? 18 : 6), false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
-    else tc_stage_act_pro<SPLIT, 4, false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
+    if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, (SPLIT ? 16 : 4)>(Xh, Xl, csx, q, b, t0);
+    else if constexpr (MODE == CRK_CONV_FAST) tc_stage_act_pro<SPLIT, (SPLIT ? 9 : 5), false, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
+    else tc_stage_act_pro<SPLIT, 4, true, false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
     tc::fence_proxy_async_smem();
     __syncthreads();
     dbg_stamp(q.dbg, 1);
@@ -270,7 +279,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     }
     __syncthreads();
     dbg_stamp(q.dbg, 3);
-    if (q.gate) {
+    if constexpr (MODE == CRK_CONV_GATE) {
         // lanes over gate pairs (2 z channels each): TaSb read and DG write are one float4 per lane
         const int nlive = min(CRK_TC_TM, p.T - t0);
         const size_t row0 = (size_t)b * p.T + t0;
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
                 reinterpret_cast<float2*>(q.g_Z + (row0 + rr) * 64)[qi] = make_float2(ts[u].x * ts[u].z, ts[u].y * ts[u].w);
             }
         }
-    } else if (q.vec_epi) {
+    } else if constexpr (MODE == CRK_CONV_FAST) {
         // 128-bit epilogue: one float4 (4 output channels of a frame) per thread per slot, U slots in
         // flight, so the side inputs of a whole 128 x 64 tile (dgrad: residual grad + dropout
         // multiplier) need 1-2 global round trips instead of 8
@@ -391,7 +400,8 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     tc::tc_fence_before();
     __syncthreads();
     dbg_stamp(q.dbg, 4);
-    if (timeout_s && threadIdx.x == 0) (q.gate ? q.g_DG : p.Y)[((size_t)b * p.T + t0) * (q.gate ? 128 : p.ldy)] = __int_as_float(0x7fc00000);
+    if (timeout_s && threadIdx.x == 0)
+        (MODE == CRK_CONV_GATE ? q.g_DG : p.Y)[((size_t)b * p.T + t0) * (MODE == CRK_CONV_GATE ? 128 : p.ldy)] = __int_as_float(0x7fc00000);
     if (warp == 1) tc::tmem_dealloc<128>(tmem);
 }
 
@@ -409,19 +419,20 @@ inline bool conv_tc_ok(const ConvTcParams& q, bool split) {
            (q.p.k - 1) * q.p.dil <= 32 && conv_tc_smem(q, split) <= 220 * 1024;
 }
 
-template <bool SPLIT>
+template <bool SPLIT, int MODE>
 inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv_tc<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_conv_tc<SPLIT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const int tiles = q.p.B * cdiv(q.p.T, CRK_TC_TM);
-    TimedLaunch tl(CRK_K_CONV, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.Cout * q.p.k);
+    TimedLaunch tl(MODE == CRK_CONV_GATE ? CRK_K_BWD_GATE : CRK_K_CONV, s,
+                   MODE == CRK_CONV_GATE ? 2.0 * q.p.B * q.p.T * 128.0 * 64 : 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.Cout * q.p.k);
     ConvTcParams qq = q;
-    qq.dbg = dbg_take(CRK_K_CONV);
-    cudaError_t le = launch_pdl(k_conv_tc<SPLIT>, dim3(tiles), dim3(256), conv_tc_smem(q, SPLIT), s, qq);
+    qq.dbg = MODE == CRK_CONV_GATE ? 0 : dbg_take(CRK_K_CONV);
+    cudaError_t le = launch_pdl(k_conv_tc<SPLIT, MODE>, dim3(tiles), dim3(256), conv_tc_smem(q, SPLIT), s, qq);
     if (le != cudaSuccess) return le;
     return launch_check();
 }
@@ -433,12 +444,16 @@ inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc,
         ConvTcParams q;
         q.p = p; q.Wtc = wtc; q.Kpad = kpad; q.Npad = npad; q.dbg = 0; q.gate = 0;
         auto al = [](const float* ptr, int ld) { return ptr == nullptr || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)); };
-        q.opt_stage = !(opt_disable_mask() & 16);
-        q.vec_epi = !(opt_disable_mask() & 4) && (p.Cout & 3) == 0 && p.Y != nullptr && al(p.Y, p.ldy) && al(p.mul_src, p.ldmul) &&
+        q.opt_stage = 0;
+        q.vec_epi = (p.Cout & 3) == 0 && p.Y != nullptr && al(p.Y, p.ldy) && al(p.mul_src, p.ldmul) &&
                     al(p.R, p.ldr) && al(p.dact_src, p.lddact);
+        const bool fast = !(opt_disable_mask() & 4) && q.vec_epi && p.xmul == nullptr && (p.Cin & 3) == 0 && al(p.X, p.ldx) && p.X != nullptr;
         q.g_dH = q.g_dS = q.g_TaSb = nullptr; q.g_DG = q.g_GOS = q.g_Z = nullptr;
         const bool split = mode == CRK_PREC_TF32X3;
-        if (conv_tc_ok(q, split)) return split ? launch_conv_tc_t<true>(q, s) : launch_conv_tc_t<false>(q, s);
+        if (conv_tc_ok(q, split)) {
+            if (fast) return split ? launch_conv_tc_t<true, CRK_CONV_FAST>(q, s) : launch_conv_tc_t<false, CRK_CONV_FAST>(q, s);
+            return split ? launch_conv_tc_t<true, CRK_CONV_GENERIC>(q, s) : launch_conv_tc_t<false, CRK_CONV_GENERIC>(q, s);
+        }
     }
     return launch_conv(p, cpt, s);
 }
@@ -454,21 +469,9 @@ inline bool gate_bwd_tc(const ResBwdGateParams& g, const float* wos_tct, cudaStr
     q.g_dH = g.dH; q.g_dS = g.dS; q.g_TaSb = g.TaSb; q.g_DG = g.DG; q.g_GOS = g.GOS; q.g_Z = g.Z;
     const bool split = mode == CRK_PREC_TF32X3;
     if (conv_tc_smem(q, split) > 220 * 1024) return false;
-    if (split) {
-        static bool a1 = false;
-        if (!a1) { *err = cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); if (*err) return true; a1 = true; }
-        TimedLaunch tl(CRK_K_BWD_GATE, s, 2.0 * g.B * g.T * 128.0 * 64);
-        *err = launch_pdl(k_conv_tc<true>, dim3(g.B * cdiv(g.T, CRK_TC_TM)), dim3(256), conv_tc_smem(q, true), s, q);
-        if (*err) return true;
-    } else {
-        static bool a2 = false;
-        if (!a2) { *err = cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); if (*err) return true; a2 = true; }
-        TimedLaunch tl(CRK_K_BWD_GATE, s, 2.0 * g.B * g.T * 128.0 * 64);
-        *err = launch_pdl(k_conv_tc<false>, dim3(g.B * cdiv(g.T, CRK_TC_TM)), dim3(256), conv_tc_smem(q, false), s, q);
-        if (*err) return true;
-    }
-    *err = launch_check();
+    *err = split ? launch_conv_tc_t<true, CRK_CONV_GATE>(q, s) : launch_conv_tc_t<false, CRK_CONV_GATE>(q, s);
     return true;
 }
+
 
 }  // namespace crk

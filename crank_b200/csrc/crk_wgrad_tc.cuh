@@ -40,12 +40,13 @@ struct WgRegs {
     float4 m[NB];
 };
 
-template <int NB>
+// VECONLY: host-checked (16 B aligned rows, ncols % 4 == 0) -> the scalar tail path is compiled out
+template <int NB, bool VECONLY = false>
 __device__ __forceinline__ void wg_load(WgRegs<NB>& R, int nrows_pad, const float* __restrict__ src, int ld, int ncols,
                                         int b, int T, int t0, int shift, const float* __restrict__ mul, int ldmul) {
     const int total = CRK_WG_TF * (nrows_pad >> 2);
-    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
-                     (mul == nullptr || (((ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mul) & 15) == 0)));
+    const bool vec = VECONLY || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                     (mul == nullptr || (((ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mul) & 15) == 0))));
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
         const int idx = threadIdx.x + u * 256;
@@ -58,10 +59,10 @@ __device__ __forceinline__ void wg_load(WgRegs<NB>& R, int nrows_pad, const floa
             const int tt = tg + shift;
             if (tg < T && tt >= 0 && tt < T && c < ncols) {
                 const size_t row = (size_t)b * T + tt;
-                if (vec && c + 3 < ncols) {
+                if (VECONLY || (vec && c + 3 < ncols)) {
                     R.v[u] = __ldg(reinterpret_cast<const float4*>(src + row * ld + c));
                     if (mul) R.m[u] = __ldg(reinterpret_cast<const float4*>(mul + row * ldmul + c));
-                } else {
+                } else if (!VECONLY) {
                     float t4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
@@ -105,7 +106,7 @@ __device__ __forceinline__ void wg_store(const WgRegs<NB>& R, float* hi, float* 
     }
 }
 
-template <bool SPLIT, int NX>
+template <bool SPLIT, int NX, bool VEC>
 __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(const WgradTcParams q) {
     const WgradParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     auto load_x = [&](int tile, int j) {
         const int bb = tile / tiles_per_utt;
         const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
-        wg_load<NX>(RX, q.Npad, p.X, p.ldx, p.Cin, bb, p.T, tt0, j * p.dil - p.padl, p.xmul, p.ldxmul);
+        wg_load<NX, VEC>(RX, q.Npad, p.X, p.ldx, p.Cin, bb, p.T, tt0, j * p.dil - p.padl, p.xmul, p.ldxmul);
     };
     auto store_x = [&](int slot) {
         wg_store<SPLIT, NX>(RX, slot_hi(slot), slot_lo(slot), csx, q.Npad, p.pro_act, p.pro_slope, p.pro_scale);
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     auto load_g = [&](int tile) {
         const int bb = tile / tiles_per_utt;
         const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
-        wg_load<8>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
+        wg_load<8, VEC>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
     };
 
     if (tile_beg < tile_end) { load_g(tile_beg); load_x(tile_beg, 0); }
@@ -285,12 +286,12 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
 // operand tile is produced from that copy (shared -> shared).
 //   xraw[r][c]  (row stride Npad + 4 floats: the 128-bit reads of 8 consecutive rows hit 8 distinct
 //   bank groups), r <-> input time t0 - padl + r, zero outside [0, T).
-template <int NR>
+template <int NR, bool VECONLY>
 __device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, const float* __restrict__ src, int ld,
                                             int ncols, int b, int T, int tstart, const float* __restrict__ mul, int ldmul) {
     const int total = rows * c4n;
-    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
-                     (mul == nullptr || (((ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mul) & 15) == 0)));
+    const bool vec = VECONLY || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                     (mul == nullptr || (((ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mul) & 15) == 0))));
 #pragma unroll
     for (int u = 0; u < NR; ++u) {
         const int idx = threadIdx.x + u * 256;
@@ -302,10 +303,10 @@ __device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, co
             const int tt = tstart + r;
             if (tt >= 0 && tt < T && c < ncols) {
                 const size_t row = (size_t)b * T + tt;
-                if (vec && c + 3 < ncols) {
+                if (VECONLY || (vec && c + 3 < ncols)) {
                     R.v[u] = __ldg(reinterpret_cast<const float4*>(src + row * ld + c));
                     if (mul) R.m[u] = __ldg(reinterpret_cast<const float4*>(mul + row * ldmul + c));
-                } else {
+                } else if (!VECONLY) {
                     float t4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
@@ -366,7 +367,7 @@ __device__ __forceinline__ void wg_transpose_raw(const float* xraw, int stride, 
     }
 }
 
-template <bool SPLIT, int NX>
+template <bool SPLIT, int NX, bool VEC>
 __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) {
     constexpr int NR = NX == 4 ? 6 : 10;                   // raw-tile float4 per thread (host checks the fit)
     const WgradParams& p = q.p;
@@ -426,8 +427,8 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     auto load_tile = [&](int tile) {
         const int bb = tile / tiles_per_utt;
         const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
-        wg_load<8>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
-        wg_load_raw<NR>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
+        wg_load<8, VEC>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
+        wg_load_raw<NR, VEC>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
     };
 
     long long dbg_acc[3] = {0, 0, 0};                      // thread 64: slot waits / transposition / barrier
@@ -543,18 +544,23 @@ inline bool wgrad_raw_ok(const WgradParams& p, int Npad, bool split) {
     if ((CRK_WG_TF + (p.k - 1) * p.dil) * (Npad >> 2) > nr * 256) return false;
     return wgrad_raw_nslot(Npad, p.k, p.dil, split) >= 2;
 }
-template <bool SPLIT, int NX>
+// 128-bit loads legal for both operands (and the multiplier): lets the kernels drop their scalar paths
+inline bool wgrad_vec_ok(const WgradParams& p) {
+    auto al = [](const float* ptr, int ld) { return ptr == nullptr || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)); };
+    return (p.Cin & 3) == 0 && (p.N & 3) == 0 && al(p.X, p.ldx) && al(p.G, p.ldg) && al(p.xmul, p.ldxmul);
+}
+template <bool SPLIT, int NX, bool VEC>
 inline cudaError_t launch_wgrad_tc_raw_nx(const WgradTcParams& q, int nchunk, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc_raw<SPLIT, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc_raw<SPLIT, NX, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const size_t g = (size_t)16 * 129 * 4 * (SPLIT ? 2 : 1), x = (size_t)16 * tc::chunk_rows(q.Npad) * 4 * (SPLIT ? 2 : 1);
     const size_t smem = (g + q.nslot * x + wgrad_raw_floats(q.Npad, q.p.k, q.p.dil)) * sizeof(float);
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
-    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX>, dim3(nchunk), dim3(256), smem, s, q);
+    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC>, dim3(nchunk), dim3(256), smem, s, q);
     if (le != cudaSuccess) return le;
     return launch_check();
 }
@@ -584,22 +590,30 @@ inline WgradTcWork wgrad_tc_work(int B, int T) {
     return w;
 }
 
-template <bool SPLIT, int NX>
+template <bool SPLIT, int NX, bool VEC>
 inline cudaError_t launch_wgrad_tc_nx(const WgradTcParams& q, int nchunk, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<SPLIT, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<SPLIT, NX, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
-    cudaError_t le = launch_pdl(k_wgrad_tc<SPLIT, NX>, dim3(nchunk), dim3(256), wgrad_tc_smem(q.Npad, SPLIT), s, q);
+    cudaError_t le = launch_pdl(k_wgrad_tc<SPLIT, NX, VEC>, dim3(nchunk), dim3(256), wgrad_tc_smem(q.Npad, SPLIT), s, q);
     if (le != cudaSuccess) return le;
     return launch_check();
 }
 template <bool SPLIT>
 inline cudaError_t launch_wgrad_tc_t(const WgradTcParams& q, int nchunk, cudaStream_t s) {
-    return q.Npad <= 64 ? launch_wgrad_tc_nx<SPLIT, 4>(q, nchunk, s) : launch_wgrad_tc_nx<SPLIT, 8>(q, nchunk, s);
+    if (wgrad_vec_ok(q.p))
+        return q.Npad <= 64 ? launch_wgrad_tc_nx<SPLIT, 4, true>(q, nchunk, s) : launch_wgrad_tc_nx<SPLIT, 8, true>(q, nchunk, s);
+    return q.Npad <= 64 ? launch_wgrad_tc_nx<SPLIT, 4, false>(q, nchunk, s) : launch_wgrad_tc_nx<SPLIT, 8, false>(q, nchunk, s);
+}
+template <bool SPLIT>
+inline cudaError_t launch_wgrad_tc_raw_t(const WgradTcParams& q, int nchunk, cudaStream_t s) {
+    if (wgrad_vec_ok(q.p))
+        return q.Npad <= 64 ? launch_wgrad_tc_raw_nx<SPLIT, 4, true>(q, nchunk, s) : launch_wgrad_tc_raw_nx<SPLIT, 8, true>(q, nchunk, s);
+    return q.Npad <= 64 ? launch_wgrad_tc_raw_nx<SPLIT, 4, false>(q, nchunk, s) : launch_wgrad_tc_raw_nx<SPLIT, 8, false>(q, nchunk, s);
 }
 
 // fused_bias: the caller wants the bias-gradient partial behind each chunk's weight partial; *bias_done
@@ -619,8 +633,7 @@ inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, in
     *nchunk = w.nchunk;
     if (wgrad_raw_ok(p, Npad, split)) {
         q.nslot = wgrad_raw_nslot(Npad, p.k, p.dil, split);
-        if (split) *err = Npad <= 64 ? launch_wgrad_tc_raw_nx<true, 4>(q, w.nchunk, s) : launch_wgrad_tc_raw_nx<true, 8>(q, w.nchunk, s);
-        else *err = Npad <= 64 ? launch_wgrad_tc_raw_nx<false, 4>(q, w.nchunk, s) : launch_wgrad_tc_raw_nx<false, 8>(q, w.nchunk, s);
+        *err = split ? launch_wgrad_tc_raw_t<true>(q, w.nchunk, s) : launch_wgrad_tc_raw_t<false>(q, w.nchunk, s);
         return true;
     }
     *err = split ? launch_wgrad_tc_t<true>(q, w.nchunk, s) : launch_wgrad_tc_t<false>(q, w.nchunk, s);

@@ -21,7 +21,7 @@ def launches():
         cnt[name] += 1
     T = sum(tot.values())
     out = [f"# ncu launch list, bench.py --precision {PREC} --batch 64 (one train step after 3 warm-up steps)", "",
-           "`ncu --metrics gpu__time_duration.sum --clock-control none -s 3700 -c 1300` (profiles/run_ncu.sh).",
+           "`ncu --metrics gpu__time_duration.sum --clock-control none -s <3 warm-up steps> -c <one step>` (profiles/*.sh).",
            "Per-launch times are cold-cache and serialised: read the SHARES.", "",
            f"{sum(cnt.values())} launches, {T/1e3:.2f} ms of device time", "",
            "| kernel | launches | total us | share | avg us |", "|---|---:|---:|---:|---:|"]
@@ -64,8 +64,10 @@ def full(kernel):
 
 with open(os.path.join(ROOT, "profiles", f"launches_{ROUND}_{PREC}.md"), "w") as f:
     f.write(launches() + "\n")
-with open(os.path.join(ROOT, "profiles", f"ncu_full_{ROUND}_{PREC}.md"), "w") as f:
-    f.write(f"# ncu --set full summaries ({ROUND}, {PREC}); .ncu-rep files stay in gpurun_out/ (scratch)\n\n")
-    for k in ["k_resblock_fwd_tc", "k_conv_tc", "k_wgrad_tc", "k_vq_argmin"]:
-        f.write(full(k) + "\n")
+KERNELS = ["k_resblock_fwd_tc", "k_conv_tc", "k_wgrad_tc", "k_vq_argmin"]
+if any(os.path.exists(os.path.join(OUT, f"prof_{k}_{PREC}.ncu-rep")) for k in KERNELS):   # keep the last summary otherwise
+    with open(os.path.join(ROOT, "profiles", f"ncu_full_{ROUND}_{PREC}.md"), "w") as f:
+        f.write(f"# ncu --set full summaries ({ROUND}, {PREC}); .ncu-rep files stay in gpurun_out/ (scratch)\n\n")
+        for k in KERNELS:
+            f.write(full(k) + "\n")
 print(open(os.path.join(ROOT, "profiles", f"launches_{ROUND}_{PREC}.md")).read()[:3000])
