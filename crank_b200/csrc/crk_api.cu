@@ -108,6 +108,16 @@ int crk_tc_probe(const float* A, int lda, int rowsA, const float* B, int ldb, in
     return CRK_OK;
 }
 
+int crk_tc_mma_rate(int N, int K, int reps, int split, int grid, long long* cycles, void* stream) {
+    if (!cycles || N < 16 || N > 128 || (N % 16) != 0 || K < 8 || K > 128 || (K % 8) != 0 || reps == 0 || grid < 1) return CRK_ERR_ARG;
+    const size_t smem = (size_t)2 * (K / 4) * (137 * 4 + tc::chunk_rows(N) * 4) * sizeof(float);
+    if (smem > 220 * 1024) return CRK_ERR_UNSUPPORTED;
+    API_TRY(cudaFuncSetAttribute(k_tc_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    k_tc_mma_rate<<<grid, 128, smem, (cudaStream_t)stream>>>(N, K, reps, split, cycles);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+
 // ---- WaveNet stack ---------------------------------------------------------------------------
 int crk_wavenet_describe(const crk_wavenet_cfg* cfg, crk_conv_desc* descs, int* n_convs,
                          long long* theta_floats, long long* weff_floats) {

@@ -154,8 +154,13 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     const ConvParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
-    __shared__ uint64_t bar_full[2];
-    __shared__ uint64_t bar_free[2];
+    // weight ring: NSLOT slots of SEG K-chunks (SEG * 4 channels).  Measured: 4 slots x 32 channels is SLOWER
+    // than 2 x 64 (dgrad k5: MMA phase 32K vs 27K cycles) -- the per-step cost (barrier round trip, pass
+    // prologues of the issue loop) outweighs the deeper prefetch; the weight bytes are not the bottleneck
+    // (issuer wait for weights: 3K of the 27K cycles).
+    constexpr int NSLOT = 2, SEG = 16;
+    __shared__ uint64_t bar_full[NSLOT];
+    __shared__ uint64_t bar_free[NSLOT];
     __shared__ uint64_t bar_acc;
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
@@ -168,29 +173,29 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     const int csx = tc::chunk_rows(rowsX) * 4;                 // floats per A chunk
     const int kch = q.Kpad >> 2;                               // A / B chunks over the whole K
     const int csw = tc::chunk_rows(q.Npad) * 4;                // floats per B chunk
-    const int nseg = (q.Kpad + 63) >> 6;                       // 64-channel K segments
+    const int nseg = (kch + SEG - 1) / SEG;                    // 32-channel K segments
     const int whalf_tap = kch * csw;                           // floats of the hi half of one tap blob
-    const int seg_max = (kch < 16 ? kch : 16) * csw;           // floats of one segment half in a slot
+    const int seg_max = (kch < SEG ? kch : SEG) * csw;         // floats of one segment half in a slot
     float* Xh = smem;
     float* Xl = Xh + kch * csx;
     float* ring = Xl + (SPLIT ? kch * csx : 0);
-    float* slot_hi[2] = {ring, ring + (SPLIT ? 2 : 1) * seg_max};
-    float* slot_lo[2] = {ring + seg_max, ring + 3 * seg_max};
+    auto slot_hi = [&](int sl) -> float* { return ring + sl * (SPLIT ? 2 : 1) * seg_max; };
+    auto slot_lo = [&](int sl) -> float* { return ring + sl * (SPLIT ? 2 : 1) * seg_max + seg_max; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsteps = p.k * nseg;
 
     // step -> (tap j, K segment sg): TMA bulk copy of that slice of the tap's blob into a ring slot
     auto produce = [&](int step) {
         const int j = step / nseg, sg = step - j * nseg;
-        const int ch0 = sg * 16;
-        const int nch = (kch - ch0) < 16 ? (kch - ch0) : 16;
+        const int ch0 = sg * SEG;
+        const int nch = (kch - ch0) < SEG ? (kch - ch0) : SEG;
         const float* blob = q.Wtc + (size_t)j * 2 * whalf_tap + (size_t)ch0 * csw;
-        tc_bulk_blob<SPLIT>(slot_hi[step & 1], slot_lo[step & 1], blob, nch * csw, whalf_tap, &bar_full[step & 1]);
+        const int sl = step & (NSLOT - 1);
+        tc_bulk_blob<SPLIT>(slot_hi(sl), slot_lo(sl), blob, nch * csw, whalf_tap, &bar_full[sl]);
     };
 
     if (threadIdx.x == 0) {
-        tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
-        tc::mbar_init(&bar_free[0], 1); tc::mbar_init(&bar_free[1], 1);
+        for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_free[i], 1); }
         tc::mbar_init(&bar_acc, 1);
         tc::fence_mbar_init();
         timeout_s = 0;
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     pdl_wait();
     dbg_stamp(q.dbg, 0);
     if (threadIdx.x == 0)
-        for (int st = 0; st < 2 && st < nsteps; ++st) produce(st);
+        for (int st = 0; st < NSLOT && st < nsteps; ++st) produce(st);
     // (deeper batches were measured: no gain in the 3xTF32 mode, and the extra registers cost the plain
     //  TF32 variant its second resident CTA per SM, which matters far more)
     // the whole A tile in ONE batch of independent loads when the registers allow (3xTF32 variant: one CTA
@@ -222,9 +227,9 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     if (warp == 0) {
         if (lane == 0) {
             long long wfree = 0;
-            for (int st = 2; st < nsteps; ++st) {
+            for (int st = NSLOT; st < nsteps; ++st) {
                 const long long c0 = q.dbg ? clock64() : 0;
-                ok &= tc::mbar_wait(&bar_free[st & 1], ((st - 2) >> 1) & 1);
+                ok &= tc::mbar_wait(&bar_free[st & (NSLOT - 1)], ((st - NSLOT) / NSLOT) & 1);
                 if (q.dbg) wfree += clock64() - c0;
                 produce(st);
             }
@@ -232,28 +237,28 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
         }
         __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
+        // MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues (see tc_issue_kmajor_w)
         const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
         const uint32_t xh_s = tc::smem_u32(Xh), xl_s = tc::smem_u32(Xl);
         uint32_t acc = 0;
         long long wfull = 0;
         for (int st = 0; st < nsteps; ++st) {
             const int j = st / nseg, sg = st - j * nseg;
-            const int ch0 = sg * 16;
-            const int nch = (kch - ch0) < 16 ? (kch - ch0) : 16;
+            const int ch0 = sg * SEG;
+            const int nch = (kch - ch0) < SEG ? (kch - ch0) : SEG;
+            const int sl = st & (NSLOT - 1);
             const long long c0 = q.dbg ? clock64() : 0;
-            ok &= tc::mbar_wait(&bar_full[st & 1], (st >> 1) & 1);
+            ok &= tc::mbar_wait(&bar_full[sl], (st / NSLOT) & 1);
             if (q.dbg) wfull += clock64() - c0;
             tc::tc_fence_after();
-            tc_issue_kmajor<SPLIT>(tmem, xh_s + ch0 * csx * 4, xl_s + ch0 * csx * 4, csx * 4, j * p.dil,
-                                   tc::smem_u32(slot_hi[st & 1]), tc::smem_u32(slot_lo[st & 1]), csw * 4,
-                                   nch * 4, idesc, acc);
-            tc::umma_commit(&bar_free[st & 1]);
+            tc_issue_kmajor_w<SPLIT>(tmem, xh_s + ch0 * csx * 4, xl_s + ch0 * csx * 4, csx * 4, j * p.dil,
+                                     tc::smem_u32(slot_hi(sl)), tc::smem_u32(slot_lo(sl)), csw * 4,
+                                     nch * 4, idesc, acc);
+            if (tc::elect_one()) tc::umma_commit(&bar_free[sl]);
         }
-        tc::umma_commit(&bar_acc);
-        dbg_put(q.dbg, 8, wfull);
-      }
-      __syncwarp();
+        if (tc::elect_one()) tc::umma_commit(&bar_acc);
+        if (lane == 0) dbg_put(q.dbg, 8, wfull);
+        __syncwarp();
     }
     ok &= tc::mbar_wait(&bar_acc, 0);
     tc::tc_fence_after();
@@ -409,7 +414,7 @@ inline size_t conv_tc_smem(const ConvTcParams& q, bool split) {
     const int rowsX = CRK_TC_TM + (q.p.k - 1) * q.p.dil;
     const int kch = q.Kpad >> 2;
     const size_t a = (size_t)kch * tc::chunk_rows(rowsX) * 4;
-    const size_t seg = (size_t)(kch < 16 ? kch : 16) * tc::chunk_rows(q.Npad) * 4;
+    const size_t seg = (size_t)(kch < 16 ? kch : 16) * tc::chunk_rows(q.Npad) * 4;     // 2 ring slots of 16 chunks
     const size_t pipe = (split ? 2 : 1) * a + (split ? 4 : 2) * seg;
     const size_t stage = (size_t)CRK_TC_TM * (q.Npad | 1);      // epilogue transposition tile
     return (pipe > stage ? pipe : stage) * sizeof(float);

@@ -131,6 +131,59 @@ __device__ __forceinline__ void tc_issue_kmajor(uint32_t tmem_d, uint32_t a_hi, 
     }
 }
 
+// Warp-collective form of tc_issue_kmajor: the WHOLE warp runs the (warp-uniform) descriptor arithmetic and
+// loop, one elected lane executes the tcgen05.mma.  With a single divergent lane issuing, every operand of
+// every MMA is moved from a vector to a uniform register first (R2UR) and the loop overhead sits on the
+// critical path: measured ~50 cycles of issue cost per MMA + ~110 per pass (profiles/mma_rate.py); code
+// the compiler can prove uniform stays in the uniform datapath.
+template <bool SPLIT>
+__device__ __forceinline__ void tc_issue_kmajor_w(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_cs_bytes,
+                                                  int a_row0, uint32_t b_hi, uint32_t b_lo, uint32_t b_cs_bytes,
+                                                  int kdim, uint32_t idesc, uint32_t& acc) {
+    const int npass = SPLIT ? 3 : 1;
+    const uint32_t inc_a = (2u * a_cs_bytes) >> 4, inc_b = (2u * b_cs_bytes) >> 4;
+    const int nk = kdim >> 3;
+    const bool leader = tc::elect_one();
+    for (int pass = 0; pass < npass; ++pass) {
+        const uint32_t as = (SPLIT && pass == 0) ? a_lo : a_hi;
+        const uint32_t bs = (SPLIT && pass == 1) ? b_lo : b_hi;
+        const uint64_t da0 = tc::make_smem_desc(as + a_row0 * 16, a_cs_bytes, 128);
+        const uint64_t db0 = tc::make_smem_desc(bs, b_cs_bytes, 128);
+        uint32_t da_lo = (uint32_t)da0, db_lo = (uint32_t)db0;
+        const uint32_t da_hi = (uint32_t)(da0 >> 32), db_hi = (uint32_t)(db0 >> 32);
+#pragma unroll 4
+        for (int i = 0; i < nk; ++i) {
+            if (leader) tc::umma_tf32(tmem_d, ((uint64_t)da_hi << 32) | da_lo, ((uint64_t)db_hi << 32) | db_lo, idesc, acc);
+            acc = 1;
+            da_lo += inc_a;
+            db_lo += inc_b;
+        }
+    }
+}
+
+// TS form: A (128 rows x kdim) lives in tensor memory at columns a_hi.. / a_lo.. (one column per k element)
+template <bool SPLIT>
+__device__ __forceinline__ void tc_issue_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                            uint32_t b_cs_bytes, int kdim, uint32_t idesc, uint32_t& acc) {
+    const int npass = SPLIT ? 3 : 1;
+    const uint32_t inc_b = (2u * b_cs_bytes) >> 4;
+    const int nk = kdim >> 3;
+    for (int pass = 0; pass < npass; ++pass) {
+        uint32_t ta = (SPLIT && pass == 0) ? a_lo : a_hi;            // lo*hi, hi*lo, hi*hi
+        const uint32_t bs = (SPLIT && pass == 1) ? b_lo : b_hi;
+        const uint64_t db0 = tc::make_smem_desc(bs, b_cs_bytes, 128);
+        uint32_t db_lo = (uint32_t)db0;
+        const uint32_t db_hi = (uint32_t)(db0 >> 32);
+#pragma unroll 4
+        for (int i = 0; i < nk; ++i) {
+            tc::umma_tf32_ts(tmem_d, ta, ((uint64_t)db_hi << 32) | db_lo, idesc, acc);
+            acc = 1;
+            ta += 8;
+            db_lo += inc_b;
+        }
+    }
+}
+
 __device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float gate_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
@@ -212,8 +265,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
             }
         __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
-        // ===== MMA issuer: conv taps =====
+        // ===== MMA issuer: conv taps (warp-collective loop, one elected lane issues: tc_issue_kmajor_w) =====
         const uint32_t xh_s = tc::smem_u32(Xh), xl_s = tc::smem_u32(Xl);
         uint32_t acc = 0;
         long long wfull = 0;
@@ -222,15 +274,16 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
             ok &= tc::mbar_wait(&bar_full[j & 1], (j >> 1) & 1);
             if (q.dbg) wfull += clock64() - c0;
             tc::tc_fence_after();
-            tc_issue_kmajor<SPLIT>(tmem, xh_s, xl_s, csx * 4, j * p.dil, tc::smem_u32(slot_hi[j & 1]),
-                                   tc::smem_u32(slot_lo[j & 1]), CSW * 4, 64, idesc, acc);
-            tc::umma_commit(&bar_free[j & 1]);
+            tc_issue_kmajor_w<SPLIT>(tmem, xh_s, xl_s, csx * 4, j * p.dil, tc::smem_u32(slot_hi[j & 1]),
+                                     tc::smem_u32(slot_lo[j & 1]), CSW * 4, 64, idesc, acc);
+            if (tc::elect_one()) tc::umma_commit(&bar_free[j & 1]);
         }
-        tc::umma_commit(&bar_acc[0]);
-        if (!has_aux) tc::umma_commit(&bar_acc[1]);
-        dbg_put(q.dbg, 8, wfull);
-      }
-      __syncwarp();
+        if (tc::elect_one()) {
+            tc::umma_commit(&bar_acc[0]);
+            if (!has_aux) tc::umma_commit(&bar_acc[1]);
+        }
+        if (lane == 0) dbg_put(q.dbg, 8, wfull);
+        __syncwarp();
     }
     // ---- aux 1x1 (decoder 0): its tile reuses the X region -> all tap MMAs must have completed ----
     if (has_aux) {
@@ -243,15 +296,18 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
         tc::tc_fence_before();
         __syncthreads();
         tc::tc_fence_after();
-        if (threadIdx.x == 32) {
+        if (warp == 1) {
             const int bi = p.k;
             uint32_t acc = 1;
             ok &= tc::mbar_wait(&bar_full[bi & 1], (bi >> 1) & 1);
             tc::tc_fence_after();
-            tc_issue_kmajor<SPLIT>(tmem, tc::smem_u32(Ch), tc::smem_u32(Cl), CSW * 4, 0, tc::smem_u32(slot_hi[bi & 1]),
-                                   tc::smem_u32(slot_lo[bi & 1]), CSW * 4, q.KaPad, idesc, acc);
-            tc::umma_commit(&bar_free[bi & 1]);
-            tc::umma_commit(&bar_acc[1]);
+            tc_issue_kmajor_w<SPLIT>(tmem, tc::smem_u32(Ch), tc::smem_u32(Cl), CSW * 4, 0, tc::smem_u32(slot_hi[bi & 1]),
+                                     tc::smem_u32(slot_lo[bi & 1]), CSW * 4, q.KaPad, idesc, acc);
+            if (tc::elect_one()) {
+                tc::umma_commit(&bar_free[bi & 1]);
+                tc::umma_commit(&bar_acc[1]);
+            }
+            __syncwarp();
         }
     }
     ok &= tc::mbar_wait(&bar_acc[1], 0);
@@ -306,14 +362,14 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
     dbg_stamp(q.dbg, 3);
 
     // ---- GEMM2: [out | skip] (async) while every warp streams the saved gates out, row-coalesced ----
-    if (threadIdx.x == 32) {
+    if (warp == 1) {
         const int bi = nblobs - 1;
         uint32_t acc2 = 0;
         ok &= tc::mbar_wait(&bar_full[bi & 1], (bi >> 1) & 1);
         tc::tc_fence_after();
-        tc_issue_kmajor<SPLIT>(tmem + 128, tc::smem_u32(Zh), tc::smem_u32(Zl), CSW * 4, 0, tc::smem_u32(slot_hi[bi & 1]),
-                               tc::smem_u32(slot_lo[bi & 1]), CSW * 4, 64, idesc, acc2);
-        tc::umma_commit(&bar_acc[2]);
+        tc_issue_kmajor_w<SPLIT>(tmem + 128, tc::smem_u32(Zh), tc::smem_u32(Zl), CSW * 4, 0, tc::smem_u32(slot_hi[bi & 1]),
+                                 tc::smem_u32(slot_lo[bi & 1]), CSW * 4, 64, idesc, acc2);
+        if (tc::elect_one()) tc::umma_commit(&bar_acc[2]);
     }
     __syncwarp();
     const int nlive = min(CRK_TC_TM, p.T - t0);     // valid rows of this tile

@@ -108,4 +108,92 @@ __global__ void __launch_bounds__(128) k_tc_probe(const TcProbeParams p) {
     if (warp == 0) tc::tmem_dealloc<128>(tmem);
 }
 
+
+// ---- MMA-rate microbenchmark ---------------------------------------------------------------------
+// Every CTA issues `reps` groups of (npass x K/8) 128 x N x 8 TF32 MMAs on zero-filled operand tiles laid
+// out exactly like the conv kernels' (A: 136+1 rows x K channels hi|lo, B: N rows x K hi|lo) through
+// tc_issue_kmajor, commits, and waits; cycles[blockIdx] = clock64 span of thread 0 from the first issue to the
+// completion barrier.  Answers "what does one MMA of this shape cost in the pipeline" (execution, not issue:
+// the issuing thread runs ahead of the tensor pipe), per N, with grid = 1 or one CTA per SM.
+template <bool SPLIT> __device__ __forceinline__ void tc_issue_kmajor(uint32_t, uint32_t, uint32_t, uint32_t, int, uint32_t, uint32_t, uint32_t, int, uint32_t, uint32_t&);
+template <bool SPLIT> __device__ __forceinline__ void tc_issue_kmajor_w(uint32_t, uint32_t, uint32_t, uint32_t, int, uint32_t, uint32_t, uint32_t, int, uint32_t, uint32_t&);
+template <bool SPLIT> __device__ __forceinline__ void tc_issue_ts(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int, uint32_t, uint32_t&);
+
+__global__ void __launch_bounds__(128) k_tc_mma_rate(int N, int K, int reps, int split, long long* __restrict__ cycles) {
+    extern __shared__ float4 crk_smem4[];
+    float* smem = reinterpret_cast<float*>(crk_smem4);
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base;
+    const int rowsA = 137, csA = rowsA * 4, csB = tc::chunk_rows(N) * 4;
+    const int kch = K >> 2;
+    float* a_hi = smem;
+    float* a_lo = a_hi + kch * csA;
+    float* b_hi = a_lo + kch * csA;
+    float* b_lo = b_hi + kch * csB;
+    const int total = 2 * kch * (csA + csB);
+    // reps < 0: pseudo-random operand data instead of zeros (is the MMA cost data dependent?)
+    const bool rnd = reps < 0;
+    if (rnd) reps = -reps;
+    for (int i = threadIdx.x; i < total; i += blockDim.x)
+        smem[i] = rnd ? (float)((i * 2654435761u) >> 8) * (1.0f / 8388608.0f) - 1.0f : 0.f;
+    if (threadIdx.x == 0) { tc::mbar_init(&mbar, 1); tc::fence_mbar_init(); }
+    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc<256>(&tmem_base);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base;
+    const int a_tmem = (split >> 1) & 1;           // bit 1 of `split`: A operand from tensor memory (columns 128..)
+    const int commit_each = (split >> 2) & 1;      // bit 2: tcgen05.commit to a scratch mbarrier after every group
+    const int warp_issue = (split >> 3) & 1;       // bit 3: warp-collective issue (uniform datapath), elected lane
+    split &= 1;
+    __shared__ uint64_t scratch_bar;
+    if (threadIdx.x == 0) tc::mbar_init(&scratch_bar, 1);
+    if (a_tmem) {                                  // zero A region: 128 lanes x 128 columns
+        float z[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = 0.f;
+        for (int c = 0; c < 128; c += 32) tc::tmem_st32(tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + 128 + c, z);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+    }
+    long long c0 = 0;
+    if (warp_issue) {
+        if ((threadIdx.x >> 5) == 0) {
+            const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, 0);
+            uint32_t acc = 0;
+            c0 = clock64();
+            for (int r = 0; r < reps; ++r) {
+                if (split) tc_issue_kmajor_w<true>(tmem, tc::smem_u32(a_hi), tc::smem_u32(a_lo), csA * 4, r & 7, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K, idesc, acc);
+                else tc_issue_kmajor_w<false>(tmem, tc::smem_u32(a_hi), tc::smem_u32(a_lo), csA * 4, r & 7, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K, idesc, acc);
+            }
+            if (tc::elect_one()) tc::umma_commit(&mbar);
+            if (threadIdx.x == 0) cycles[2 * blockIdx.x + 1] = clock64() - c0;
+            __syncwarp();
+        }
+    } else if (threadIdx.x == 0) {
+        const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, 0);
+        uint32_t acc = 0;
+        c0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            if (a_tmem) {
+                if (split) tc_issue_ts<true>(tmem, tmem + 128, tmem + 128 + 64, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K > 64 ? 64 : K, idesc, acc);
+                else tc_issue_ts<false>(tmem, tmem + 128, tmem + 128 + 64, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K > 64 ? 64 : K, idesc, acc);
+            } else if (split) tc_issue_kmajor<true>(tmem, tc::smem_u32(a_hi), tc::smem_u32(a_lo), csA * 4, r & 7, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K, idesc, acc);
+            else tc_issue_kmajor<false>(tmem, tc::smem_u32(a_hi), tc::smem_u32(a_lo), csA * 4, r & 7, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K, idesc, acc);
+            if (commit_each) tc::umma_commit(&scratch_bar);
+        }
+        tc::umma_commit(&mbar);
+        cycles[2 * blockIdx.x + 1] = clock64() - c0;          // issue time of the whole batch
+    }
+    const bool ok = tc::mbar_wait(&mbar, 0);
+    tc::tc_fence_after();
+    if (threadIdx.x == 0) cycles[2 * blockIdx.x] = ok ? clock64() - c0 : -1;
+    tc::tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc<256>(tmem);
+}
+
 }  // namespace crk

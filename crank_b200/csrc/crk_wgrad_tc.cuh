@@ -201,13 +201,16 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
         tc::tc_fence_after();
         if (tile == tile_beg) dbg_stamp(q.dbg, 2);
         for (int j = 0; j < p.k; ++j, ++step) {
-            if (threadIdx.x == 32) {
+            if (warp == 1) {                               // warp-collective issue, one elected lane (tc_issue_kmajor_w)
                 uint32_t acc = ntile_done > 0 ? 1u : 0u;
                 // A = G^T (M = 128 rows = co), B = X_j^T (N rows = ci), K = 64 frames
-                tc_issue_kmajor<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi(step % NS)),
-                                       tc::smem_u32(slot_lo(step % NS)), csx * 4, CRK_WG_TF, idesc, acc);
-                tc::umma_commit(&bar_slot[step % NS]);
-                if (j == p.k - 1) tc::umma_commit(&bar_tile);
+                tc_issue_kmajor_w<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi(step % NS)),
+                                         tc::smem_u32(slot_lo(step % NS)), csx * 4, CRK_WG_TF, idesc, acc);
+                if (tc::elect_one()) {
+                    tc::umma_commit(&bar_slot[step % NS]);
+                    if (j == p.k - 1) tc::umma_commit(&bar_tile);
+                }
+                __syncwarp();
             }
             if (j + 1 < p.k) {
                 const int nstep = step + 1;
@@ -464,12 +467,15 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
             __syncthreads();
             tc::tc_fence_after();
             if (dbg64) { dbg_acc[0] += c1 - c0; dbg_acc[1] += c2 - c1; dbg_acc[2] += clock64() - c2; }
-            if (threadIdx.x == 32) {
+            if (warp == 1) {                               // warp-collective issue, one elected lane (tc_issue_kmajor_w)
                 uint32_t acc = ntile_done > 0 ? 1u : 0u;
-                tc_issue_kmajor<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi(sl)),
-                                       tc::smem_u32(slot_lo(sl)), csx * 4, CRK_WG_TF, idesc, acc);
-                tc::umma_commit(&bar_slot[sl]);
-                if (j == p.k - 1) tc::umma_commit(&bar_tile);
+                tc_issue_kmajor_w<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi(sl)),
+                                         tc::smem_u32(slot_lo(sl)), csx * 4, CRK_WG_TF, idesc, acc);
+                if (tc::elect_one()) {
+                    tc::umma_commit(&bar_slot[sl]);
+                    if (j == p.k - 1) tc::umma_commit(&bar_tile);
+                }
+                __syncwarp();
             }
         }
         if (tile == tile_beg) dbg_stamp(q.dbg, 3);

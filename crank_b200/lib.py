@@ -62,6 +62,7 @@ SIGNATURES = {
     "crk_timing_read": (i32, [C.POINTER(i32), C.POINTER(f32)]),
     "crk_timing_flops": (C.c_double, []),
     "crk_tc_probe": (i32, [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "crk_tc_mma_rate": (i32, [i32, i32, i32, i32, i32, vp, vp]),
     "crk_wavenet_describe": (i32, [PW, PD, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
     "crk_wavenet_act_floats": (i64, [PW, i32, i32]),
     "crk_wavenet_ws_floats": (i64, [PW, i32, i32]),
