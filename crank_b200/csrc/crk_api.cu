@@ -287,8 +287,9 @@ int crk_vq_ema(const float* counts, const float* esum, float* ema_size, float* e
     // python-double scalars of the reference, rounded once to fp32 like torch does for scalar operands
     const float one_m_decay = (float)(1.0 - (double)decay);
     const float keps = (float)((double)K * (double)eps);
-    k_vq_ema<<<1, 512, 0, (cudaStream_t)stream>>>(counts, esum, ema_size, ema_w, W, decay, one_m_decay, eps,
-                                                   keps, K, D);
+    k_vq_ema_size<<<1, 512, 0, (cudaStream_t)stream>>>(counts, ema_size, decay, one_m_decay, eps, keps, K);
+    API_TRY(launch_check());
+    k_vq_ema_w<<<cdiv(K * D, 256), 256, 0, (cudaStream_t)stream>>>(esum, ema_size, ema_w, W, decay, one_m_decay, K, D);
     API_TRY(launch_check());
     return CRK_OK;
 }
@@ -355,7 +356,9 @@ static int stft_params(StftParams* p, const float* x, int ldx, const float* y, i
 }
 long long crk_stft_loss_ws_floats(int B, int T, int D, int n_fft, int hop) {
     if (B < 1 || T < 1 || D < 1 || n_fft < 2 || hop < 1) return -1;
-    return 2LL * loss_blocks((long long)B * (1 + T / hop) * (n_fft / 2 + 1) * D);
+    const long long a = 2LL * loss_blocks((long long)B * (1 + T / hop) * (n_fft / 2 + 1) * D);
+    const long long f = 2LL * B * (1 + T / hop);             // frame-per-CTA kernel: one partial pair per frame
+    return a > f ? a : f;
 }
 int crk_stft_loss_fwd(const float* x, int ldx, const float* y, int ldy, int B, int T, int D,
                       int n_fft, int hop, int win, float* out, float* ws, void* stream) {
@@ -364,9 +367,17 @@ int crk_stft_loss_fwd(const float* x, int ldx, const float* y, int ldy, int B, i
     if (rc) return rc;
     if (!out || !ws) return CRK_ERR_ARG;
     const long long N = (long long)B * p.M * p.bins * D;
-    const int nblk = loss_blocks(N);
-    const size_t smem = (size_t)3 * n_fft * sizeof(float);
-    k_stft_loss_part<<<nblk, CRK_THREADS, smem, (cudaStream_t)stream>>>(p, ws);
+    int nblk = loss_blocks(N);
+    const size_t fsmem = stft_frame_smem_bytes(n_fft, win, D, false);
+    if (fsmem <= 160 * 1024 && (long long)B * p.M <= (1 << 20)) {
+        static bool attr = false;
+        if (!attr) { API_TRY(cudaFuncSetAttribute(k_stft_loss_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+        nblk = B * p.M;
+        k_stft_loss_frame<<<nblk, CRK_THREADS, fsmem, (cudaStream_t)stream>>>(p, ws);
+    } else {
+        const size_t smem = (size_t)3 * n_fft * sizeof(float);
+        k_stft_loss_part<<<nblk, CRK_THREADS, smem, (cudaStream_t)stream>>>(p, ws);
+    }
     API_TRY(launch_check());
     k_finalize<<<1, CRK_THREADS, 0, (cudaStream_t)stream>>>(ws, nblk, 2, out, 0, -1);
     API_TRY(launch_check());
@@ -387,11 +398,18 @@ int crk_stft_loss_bwd(const float* x, int ldx, const float* y, int ldy, int B, i
         k_zero_panel<<<(unsigned)cdivl(rows * D, 256), 256, 0, s>>>(dx, lddx, D, rows);
         API_TRY(launch_check());
     }
-    const long long nfr = (long long)B * D * p.M;
-    long long nblk = cdivl(nfr, 8);
-    if (nblk > 148 * 8) nblk = 148 * 8;
-    const size_t smem = (size_t)(3 * n_fft + 16 * p.bins) * sizeof(float);
-    k_stft_loss_bwd<<<(unsigned)nblk, CRK_THREADS, smem, s>>>(p, g, glog, scale, dx, lddx);
+    const size_t fsmem = stft_frame_smem_bytes(n_fft, win, D, true);
+    if (fsmem <= 160 * 1024 && (long long)B * p.M <= (1 << 20)) {
+        static bool attr = false;
+        if (!attr) { API_TRY(cudaFuncSetAttribute(k_stft_loss_bwd_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+        k_stft_loss_bwd_frame<<<B * p.M, CRK_THREADS, fsmem, s>>>(p, g, glog, scale, dx, lddx);
+    } else {
+        const long long nfr = (long long)B * D * p.M;
+        long long nblk = cdivl(nfr, 8);
+        if (nblk > 148 * 8) nblk = 148 * 8;
+        const size_t smem = (size_t)(3 * n_fft + 16 * p.bins) * sizeof(float);
+        k_stft_loss_bwd<<<(unsigned)nblk, CRK_THREADS, smem, s>>>(p, g, glog, scale, dx, lddx);
+    }
     API_TRY(launch_check());
     return CRK_OK;
 }

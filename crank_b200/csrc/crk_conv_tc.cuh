@@ -21,7 +21,8 @@ struct ConvTcParams {
     int Kpad, Npad;       // K rounded up to 8, UMMA N (multiple of 16, <= 128)
     int dbg;
     int vec_epi;          // epilogue may use 128-bit accesses (Cout, row strides and pointers all 16 B aligned)
-    int opt_stage;        // A tile staged in one deep batch of loads
+    int opt_stage;        // (unused)
+    int kshift, nshift;   // FAST mode: log2(Kpad / 4), log2(Cout / 4)  (both powers of two there)
     // gate-backward mode (gate != 0), the tensor-core version of k_resblock_bwd_gate:
     //   A[row][4q+r] = r<2 ? sqrt(.5)*dH[row][2q+r] : dS[row][2q+r-2]  (also written to GOS),  acc = A . Wos^T = dz
     //   epilogue: dg = gate'(dz; ta, sb) -> DG (interleaved gate order),  z = ta*sb -> Z
@@ -74,9 +75,11 @@ __device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats
 // VECONLY: the host has checked that 128-bit loads are legal (the scalar fallback is compiled out: these
 // kernels execute their straight-line code once per CTA, so every unrolled path that is not taken still
 // costs instruction-cache footprint)
+// c4shift >= 0: Kpad / 4 is a power of two (index split by shift: the runtime division is ~30 instructions per
+// element in code that runs once per CTA)
 template <bool SPLIT, int U, bool HASMUL, bool VECONLY>
 __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_floats, const ConvParams& p, int Kpad,
-                                                 int b, int tstart, int rows) {
+                                                 int b, int tstart, int rows, int c4shift = -1) {
     const int c4n = Kpad >> 2;
     const int total = rows * c4n;
     const bool vec = VECONLY ||
@@ -95,7 +98,7 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
             if (HASMUL) m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
             off[u] = -1;
             if (idx < total) {
-                const int r = idx / c4n, c4 = idx - r * c4n;
+                const int r = (VECONLY && c4shift >= 0) ? (idx >> c4shift) : idx / c4n, c4 = idx - r * c4n;
                 off[u] = c4 * cs_floats + r * 4;
                 const int tt = tstart + r;
                 const int c = c4 * 4;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     // per SM, 255 registers): a batch costs ~2.4K cycles however many loads it holds (measured: 5 batches
     // of 4 = 12K cycles for the K=128 dgrad tile)
     if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, (SPLIT ? 16 : 4)>(Xh, Xl, csx, q, b, t0);
-    else if constexpr (MODE == CRK_CONV_FAST) tc_stage_act_pro<SPLIT, (SPLIT ? 9 : 5), false, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
+    else if constexpr (MODE == CRK_CONV_FAST) tc_stage_act_pro<SPLIT, (SPLIT ? 9 : 5), false, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX, q.kshift);
     else tc_stage_act_pro<SPLIT, 4, true, false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
     tc::fence_proxy_async_smem();
     __syncthreads();
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
                 const int e = e0 + u * blockDim.x;
                 mulv[u] = one4; rv[u] = zero4; dv[u] = one4; oldv[u] = zero4;
                 if (e < total) {
-                    const int rr = e / c4n, c4 = e - rr * c4n;
+                    const int rr = e >> q.nshift, c4 = e - rr * c4n;
                     const size_t row = row0 + rr;
                     if (p.mul_src) mulv[u] = __ldg(reinterpret_cast<const float4*>(p.mul_src + row * p.ldmul) + c4);
                     if (p.R) rv[u] = __ldg(reinterpret_cast<const float4*>(p.R + row * p.ldr) + c4);
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
             for (int u = 0; u < U; ++u) {
                 const int e = e0 + u * blockDim.x;
                 if (e >= total) continue;
-                const int rr = e / c4n, c4 = e - rr * c4n;
+                const int rr = e >> q.nshift, c4 = e - rr * c4n;
                 const float* sp = S + rr * sst + 4 * c4;
                 float y[4] = {sp[0], sp[1], sp[2], sp[3]};
                 const float m4[4] = {mulv[u].x, mulv[u].y, mulv[u].z, mulv[u].w};
@@ -452,7 +455,10 @@ inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc,
         q.opt_stage = 0;
         q.vec_epi = (p.Cout & 3) == 0 && p.Y != nullptr && al(p.Y, p.ldy) && al(p.mul_src, p.ldmul) &&
                     al(p.R, p.ldr) && al(p.dact_src, p.lddact);
-        const bool fast = !(opt_disable_mask() & 4) && q.vec_epi && p.xmul == nullptr && (p.Cin & 3) == 0 && al(p.X, p.ldx) && p.X != nullptr;
+        auto lg2 = [](int v) { int sft = 0; while ((1 << sft) < v) ++sft; return (1 << sft) == v ? sft : -1; };
+        q.kshift = lg2(kpad >> 2); q.nshift = lg2(p.Cout >> 2);
+        const bool fast = !(opt_disable_mask() & 4) && q.vec_epi && p.xmul == nullptr && (p.Cin & 3) == 0 && al(p.X, p.ldx) && p.X != nullptr &&
+                          q.kshift >= 0 && q.nshift >= 0;
         q.g_dH = q.g_dS = q.g_TaSb = nullptr; q.g_DG = q.g_GOS = q.g_Z = nullptr;
         const bool split = mode == CRK_PREC_TF32X3;
         if (conv_tc_ok(q, split)) {
@@ -470,7 +476,7 @@ inline bool gate_bwd_tc(const ResBwdGateParams& g, const float* wos_tct, cudaStr
     ConvTcParams q;
     q.p = conv_params_default();
     q.p.B = g.B; q.p.T = g.T; q.p.Cin = 128; q.p.Cout = 64; q.p.k = 1; q.p.dil = 1; q.p.padl = 0;
-    q.Wtc = wos_tct; q.Kpad = 128; q.Npad = 64; q.dbg = 0; q.gate = 1; q.vec_epi = 0; q.opt_stage = 0;
+    q.Wtc = wos_tct; q.Kpad = 128; q.Npad = 64; q.dbg = 0; q.gate = 1; q.vec_epi = 0; q.opt_stage = 0; q.kshift = q.nshift = -1;
     q.g_dH = g.dH; q.g_dS = g.dS; q.g_TaSb = g.TaSb; q.g_DG = g.DG; q.g_GOS = g.GOS; q.g_Z = g.Z;
     const bool split = mode == CRK_PREC_TF32X3;
     if (conv_tc_smem(q, split) > 220 * 1024) return false;

@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
 // operand tile is produced from that copy (shared -> shared).
 //   xraw[r][c]  (row stride Npad + 4 floats: the 128-bit reads of 8 consecutive rows hit 8 distinct
 //   bank groups), r <-> input time t0 - padl + r, zero outside [0, T).
-template <int NR, bool VECONLY>
+// C4L: log2(c4n) when the channel-quad count is a power of two (the index split becomes a shift; the runtime
+// division cost ~1.8K cycles per tile in the load-issue and store phases each), -1: generic
+template <int NR, bool VECONLY, int C4L>
 __device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, const float* __restrict__ src, int ld,
                                             int ncols, int b, int T, int tstart, const float* __restrict__ mul, int ldmul) {
     const int total = rows * c4n;
@@ -301,7 +303,7 @@ __device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, co
         R.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         R.m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
         if (idx < total) {
-            const int r = idx / c4n, c4 = idx - r * c4n;
+            const int r = C4L >= 0 ? (idx >> (C4L >= 0 ? C4L : 0)) : idx / c4n, c4 = idx - r * c4n;
             const int c = c4 * 4;
             const int tt = tstart + r;
             if (tt >= 0 && tt < T && c < ncols) {
@@ -325,7 +327,7 @@ __device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, co
     }
 }
 
-template <int NR>
+template <int NR, int C4L>
 __device__ __forceinline__ void wg_store_raw(const WgRegs<NR>& R, float* xraw, int stride, int c4n, int rows,
                                              int pro_act, float pro_slope, float pro_scale) {
     const int total = rows * c4n;
@@ -333,7 +335,7 @@ __device__ __forceinline__ void wg_store_raw(const WgRegs<NR>& R, float* xraw, i
     for (int u = 0; u < NR; ++u) {
         const int idx = threadIdx.x + u * 256;
         if (idx >= total) continue;
-        const int r = idx / c4n, c4 = idx - r * c4n;
+        const int r = C4L >= 0 ? (idx >> (C4L >= 0 ? C4L : 0)) : idx / c4n, c4 = idx - r * c4n;
         float4 x;
         x.x = apply_act(R.v[u].x * pro_scale, pro_act, pro_slope) * R.m[u].x;
         x.y = apply_act(R.v[u].y * pro_scale, pro_act, pro_slope) * R.m[u].y;
@@ -370,7 +372,7 @@ __device__ __forceinline__ void wg_transpose_raw(const float* xraw, int stride, 
     }
 }
 
-template <bool SPLIT, int NX, bool VEC>
+template <bool SPLIT, int NX, bool VEC, int C4L>
 __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) {
     constexpr int NR = NX == 4 ? 6 : 10;                   // raw-tile float4 per thread (host checks the fit)
     const WgradParams& p = q.p;
@@ -431,17 +433,21 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
         const int bb = tile / tiles_per_utt;
         const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
         wg_load<8, VEC>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
-        wg_load_raw<NR, VEC>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
+        wg_load_raw<NR, VEC, C4L>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
     };
 
     long long dbg_acc[3] = {0, 0, 0};                      // thread 64: slot waits / transposition / barrier
+    long long dbg_tile[5] = {0, 0, 0, 0, 0};               // per tile: bar_tile wait / G store / raw store / load issue / barrier
     if (tile_beg < tile_end) load_tile(tile_beg);
     for (int tile = tile_beg; tile < tile_end; ++tile) {
         if (tile == tile_beg) dbg_stamp(q.dbg, 0);
         // previous tile's MMAs read the G^T buffer and the ring slots; every thread has also passed the
         // barrier that follows the previous tile's last transposition, so xraw may be overwritten
+        const bool d64 = q.dbg && threadIdx.x == 64;
+        const long long t0c = d64 ? clock64() : 0;
         if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
         if (tile == tile_beg) dbg_stamp(q.dbg, 1);
+        const long long t1c = d64 ? clock64() : 0;
         wg_store<SPLIT, 8>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
         if (q.bias) {
 #pragma unroll
@@ -449,9 +455,13 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
                 bsum[u].x += RG.v[u].x; bsum[u].y += RG.v[u].y; bsum[u].z += RG.v[u].z; bsum[u].w += RG.v[u].w;
             }
         }
-        wg_store_raw<NR>(RX, xraw, rstride, c4n, rows_raw, p.pro_act, p.pro_slope, p.pro_scale);
+        const long long t2c = d64 ? clock64() : 0;
+        wg_store_raw<NR, C4L>(RX, xraw, rstride, c4n, rows_raw, p.pro_act, p.pro_slope, p.pro_scale);
+        const long long t3c = d64 ? clock64() : 0;
         if (tile + 1 < tile_end) load_tile(tile + 1);      // a whole tile (k tap iterations) of latency cover
+        const long long t4c = d64 ? clock64() : 0;
         __syncthreads();
+        if (d64) { dbg_tile[0] += t1c - t0c; dbg_tile[1] += t2c - t1c; dbg_tile[2] += t3c - t2c; dbg_tile[3] += t4c - t3c; dbg_tile[4] += clock64() - t4c; }
         if (tile == tile_beg) dbg_stamp(q.dbg, 2);
         for (int j = 0; j < p.k; ++j, ++step) {
             const int sl = step % NS;
@@ -487,7 +497,10 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     if (!ok) timeout_s = 1;
     __syncthreads();
     dbg_stamp(q.dbg, 5);
-    if (q.dbg && threadIdx.x == 64) { dbg_put(1, 8, dbg_acc[0]); dbg_put(1, 9, dbg_acc[1]); dbg_put(1, 10, dbg_acc[2]); }
+    if (q.dbg && threadIdx.x == 64) {
+        dbg_put(1, 8, dbg_acc[0]); dbg_put(1, 9, dbg_acc[1]); dbg_put(1, 10, dbg_acc[2]);
+        for (int i = 0; i < 5; ++i) dbg_put(1, 11 + i, dbg_tile[i]);
+    }
 
     // ---- epilogue (identical to k_wgrad_tc) ----
     const int co = (warp & 3) * 32 + lane;
@@ -555,18 +568,18 @@ inline bool wgrad_vec_ok(const WgradParams& p) {
     auto al = [](const float* ptr, int ld) { return ptr == nullptr || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)); };
     return (p.Cin & 3) == 0 && (p.N & 3) == 0 && al(p.X, p.ldx) && al(p.G, p.ldg) && al(p.xmul, p.ldxmul);
 }
-template <bool SPLIT, int NX, bool VEC>
+template <bool SPLIT, int NX, bool VEC, int C4L>
 inline cudaError_t launch_wgrad_tc_raw_nx(const WgradTcParams& q, int nchunk, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc_raw<SPLIT, NX, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const size_t g = (size_t)16 * 129 * 4 * (SPLIT ? 2 : 1), x = (size_t)16 * tc::chunk_rows(q.Npad) * 4 * (SPLIT ? 2 : 1);
     const size_t smem = (g + q.nslot * x + wgrad_raw_floats(q.Npad, q.p.k, q.p.dil)) * sizeof(float);
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
-    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC>, dim3(nchunk), dim3(256), smem, s, q);
+    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L>, dim3(nchunk), dim3(256), smem, s, q);
     if (le != cudaSuccess) return le;
     return launch_check();
 }
@@ -617,9 +630,11 @@ inline cudaError_t launch_wgrad_tc_t(const WgradTcParams& q, int nchunk, cudaStr
 }
 template <bool SPLIT>
 inline cudaError_t launch_wgrad_tc_raw_t(const WgradTcParams& q, int nchunk, cudaStream_t s) {
-    if (wgrad_vec_ok(q.p))
-        return q.Npad <= 64 ? launch_wgrad_tc_raw_nx<SPLIT, 4, true>(q, nchunk, s) : launch_wgrad_tc_raw_nx<SPLIT, 8, true>(q, nchunk, s);
-    return q.Npad <= 64 ? launch_wgrad_tc_raw_nx<SPLIT, 4, false>(q, nchunk, s) : launch_wgrad_tc_raw_nx<SPLIT, 8, false>(q, nchunk, s);
+    if (wgrad_vec_ok(q.p)) {
+        if (q.Npad == 64) return launch_wgrad_tc_raw_nx<SPLIT, 4, true, 4>(q, nchunk, s);     // the WaveNet blocks
+        return q.Npad <= 64 ? launch_wgrad_tc_raw_nx<SPLIT, 4, true, -1>(q, nchunk, s) : launch_wgrad_tc_raw_nx<SPLIT, 8, true, -1>(q, nchunk, s);
+    }
+    return q.Npad <= 64 ? launch_wgrad_tc_raw_nx<SPLIT, 4, false, -1>(q, nchunk, s) : launch_wgrad_tc_raw_nx<SPLIT, 8, false, -1>(q, nchunk, s);
 }
 
 // fused_bias: the caller wants the bias-gradient partial behind each chunk's weight partial; *bias_done

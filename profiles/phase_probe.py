@@ -38,7 +38,8 @@ for name, (kid, idx, labels, n) in sel.items():
     d = (t[:, 1:] - t[:, :-1]).mean(0)
     diag = {"resblock_fwd k5 d2": ["issuer wait for weights"],
             "conv dgrad k5 (K128,N64)": ["issuer wait for weights", "producer wait for free slot"],
-            "wgrad conv k5": ["slot waits", "transposition", "barrier"]}[name]
+            "wgrad conv k5": ["slot waits", "transposition", "barrier", "tile: wait prev MMAs", "tile: G store", "tile: raw store",
+                              "tile: issue next loads", "tile: barrier"]}[name]
     print("   diag (cycles, CTA mean):", {l: int(full[:, 8 + i].mean()) for i, l in enumerate(diag)})
     print(prec, name, "CTAs", len(t), {l: int(v) for l, v in zip(labels, d)}, "total", int((t[:, n - 1] - t[:, 0]).mean()),
           "kernel span", int(t[:, n - 1].max() - t[:, 0].min()))
