@@ -67,6 +67,9 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
         if (mbar_try_wait(bar, parity)) return true;
     return false;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // one arrival + expected transaction bytes (the bulk copies below complete the transaction count)
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

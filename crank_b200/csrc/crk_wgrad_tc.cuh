@@ -373,13 +373,19 @@ __device__ __forceinline__ void wg_transpose_raw(const float* xraw, int stride, 
 }
 
 template <bool SPLIT, int NX, bool VEC, int C4L>
-__global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) {
+__global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) {
+    // 9 warps: warps 0..7 ("workers") load, stage and transpose; warp 8 only issues MMAs.  With the issue
+    // inside a worker warp every tap waited ~1K cycles at the block barrier for that warp's 24 MMAs
+    // (measured: 19K of 85K cycles per CTA); now workers hand a finished slot to the issuer through an
+    // mbarrier and go straight to the next tap.
     constexpr int NR = NX == 4 ? 6 : 10;                   // raw-tile float4 per thread (host checks the fit)
+    constexpr int NWORK = 256;
     const WgradParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
-    __shared__ uint64_t bar_slot[4];
-    __shared__ uint64_t bar_tile;
+    __shared__ uint64_t bar_full[4];                       // slot written by all workers (count NWORK)
+    __shared__ uint64_t bar_slot[4];                       // the MMAs that read the slot have completed
+    __shared__ uint64_t bar_tile;                          // all MMAs of a tile have completed
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
@@ -400,6 +406,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     auto slot_hi = [&](int sl) -> float* { return ring + sl * slot_floats; };
     auto slot_lo = [&](int sl) -> float* { return ring + sl * slot_floats + xhalf; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool worker = threadIdx.x < NWORK;
 
     const int tiles_per_utt = (p.T + CRK_WG_TF - 1) / CRK_WG_TF;
     const int ntiles = p.B * tiles_per_utt;
@@ -407,7 +414,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     const int tile_end = min(ntiles, tile_beg + p.tiles_per_chunk);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) tc::mbar_init(&bar_slot[i], 1);
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&bar_slot[i], 1); tc::mbar_init(&bar_full[i], NWORK); }
         tc::mbar_init(&bar_tile, 1);
         tc::fence_mbar_init();
         timeout_s = 0;
@@ -417,68 +424,66 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
-    const uint32_t gh_s = tc::smem_u32(Gh), gl_s = tc::smem_u32(Gl);
     bool ok = true;
-    int step = 0;
     int ntile_done = 0;
-
-    WgRegs<8> RG;
-    WgRegs<NR> RX;
     float4 bsum[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) bsum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     pdl_wait();
-    auto load_tile = [&](int tile) {
-        const int bb = tile / tiles_per_utt;
-        const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
-        wg_load<8, VEC>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
-        wg_load_raw<NR, VEC, C4L>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
-    };
 
-    long long dbg_acc[3] = {0, 0, 0};                      // thread 64: slot waits / transposition / barrier
-    long long dbg_tile[5] = {0, 0, 0, 0, 0};               // per tile: bar_tile wait / G store / raw store / load issue / barrier
-    if (tile_beg < tile_end) load_tile(tile_beg);
-    for (int tile = tile_beg; tile < tile_end; ++tile) {
-        if (tile == tile_beg) dbg_stamp(q.dbg, 0);
-        // previous tile's MMAs read the G^T buffer and the ring slots; every thread has also passed the
-        // barrier that follows the previous tile's last transposition, so xraw may be overwritten
-        const bool d64 = q.dbg && threadIdx.x == 64;
-        const long long t0c = d64 ? clock64() : 0;
-        if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
-        if (tile == tile_beg) dbg_stamp(q.dbg, 1);
-        const long long t1c = d64 ? clock64() : 0;
-        wg_store<SPLIT, 8>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
-        if (q.bias) {
+    if (worker) {
+        WgRegs<8> RG;
+        WgRegs<NR> RX;
+        auto load_tile = [&](int tile) {
+            const int bb = tile / tiles_per_utt;
+            const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
+            wg_load<8, VEC>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
+            wg_load_raw<NR, VEC, C4L>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
+        };
+        int step = 0;
+        if (tile_beg < tile_end) load_tile(tile_beg);
+        for (int tile = tile_beg; tile < tile_end; ++tile) {
+            if (tile == tile_beg) dbg_stamp(q.dbg, 0);
+            // the previous tile's MMAs read the G^T buffer and the ring slots; they were issued only after
+            // every worker had handed over its last slot, i.e. finished reading xraw -> all three are free
+            if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
+            if (tile == tile_beg) dbg_stamp(q.dbg, 1);
+            wg_store<SPLIT, 8>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
+            if (q.bias) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                bsum[u].x += RG.v[u].x; bsum[u].y += RG.v[u].y; bsum[u].z += RG.v[u].z; bsum[u].w += RG.v[u].w;
+                for (int u = 0; u < 8; ++u) {
+                    bsum[u].x += RG.v[u].x; bsum[u].y += RG.v[u].y; bsum[u].z += RG.v[u].z; bsum[u].w += RG.v[u].w;
+                }
             }
+            wg_store_raw<NR, C4L>(RX, xraw, rstride, c4n, rows_raw, p.pro_act, p.pro_slope, p.pro_scale);
+            if (tile + 1 < tile_end) load_tile(tile + 1);  // a whole tile (k tap iterations) of latency cover
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // workers only: xraw complete
+            if (tile == tile_beg) dbg_stamp(q.dbg, 2);
+            for (int j = 0; j < p.k; ++j, ++step) {
+                const int sl = step % NS;
+                // the MMAs of step - NS (this tile; earlier tiles are covered by bar_tile) read this slot
+                if (j >= NS) ok &= tc::mbar_wait(&bar_slot[sl], ((step - NS) / NS) & 1);
+                wg_transpose_raw<SPLIT, NX>(xraw, rstride, slot_hi(sl), slot_lo(sl), csx, q.Npad, j * p.dil);
+                tc::fence_proxy_async_smem();               // generic-proxy writes (G^T, slot) -> async proxy
+                tc::mbar_arrive(&bar_full[sl]);
+            }
+            if (tile == tile_beg) dbg_stamp(q.dbg, 3);
+            ++ntile_done;
         }
-        const long long t2c = d64 ? clock64() : 0;
-        wg_store_raw<NR, C4L>(RX, xraw, rstride, c4n, rows_raw, p.pro_act, p.pro_slope, p.pro_scale);
-        const long long t3c = d64 ? clock64() : 0;
-        if (tile + 1 < tile_end) load_tile(tile + 1);      // a whole tile (k tap iterations) of latency cover
-        const long long t4c = d64 ? clock64() : 0;
-        __syncthreads();
-        if (d64) { dbg_tile[0] += t1c - t0c; dbg_tile[1] += t2c - t1c; dbg_tile[2] += t3c - t2c; dbg_tile[3] += t4c - t3c; dbg_tile[4] += clock64() - t4c; }
-        if (tile == tile_beg) dbg_stamp(q.dbg, 2);
-        for (int j = 0; j < p.k; ++j, ++step) {
-            const int sl = step % NS;
-            const bool dbg64 = q.dbg && threadIdx.x == 64;
-            const long long c0 = dbg64 ? clock64() : 0;
-            // the MMAs of step - NS (this tile; earlier tiles are covered by bar_tile) read this slot
-            if (j >= NS) ok &= tc::mbar_wait(&bar_slot[sl], ((step - NS) / NS) & 1);
-            const long long c1 = dbg64 ? clock64() : 0;
-            wg_transpose_raw<SPLIT, NX>(xraw, rstride, slot_hi(sl), slot_lo(sl), csx, q.Npad, j * p.dil);
-            tc::fence_proxy_async_smem();
-            tc::tc_fence_before();
-            const long long c2 = dbg64 ? clock64() : 0;
-            __syncthreads();
-            tc::tc_fence_after();
-            if (dbg64) { dbg_acc[0] += c1 - c0; dbg_acc[1] += c2 - c1; dbg_acc[2] += clock64() - c2; }
-            if (warp == 1) {                               // warp-collective issue, one elected lane (tc_issue_kmajor_w)
-                uint32_t acc = ntile_done > 0 ? 1u : 0u;
+        dbg_stamp(q.dbg, 4);
+        if (ntile_done > 0) ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1);
+    } else {
+        // ===== MMA issuer warp =====
+        const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
+        const uint32_t gh_s = tc::smem_u32(Gh), gl_s = tc::smem_u32(Gl);
+        int step = 0;
+        for (int tile = tile_beg; tile < tile_end; ++tile) {
+            for (int j = 0; j < p.k; ++j, ++step) {
+                const int sl = step % NS;
+                ok &= tc::mbar_wait(&bar_full[sl], (step / NS) & 1);
+                tc::tc_fence_after();
+                uint32_t acc = tile > tile_beg ? 1u : 0u;
+                // A = G^T (M = 128 rows = co), B = X_j^T (N rows = ci), K = 64 frames
                 tc_issue_kmajor_w<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi(sl)),
                                          tc::smem_u32(slot_lo(sl)), csx * 4, CRK_WG_TF, idesc, acc);
                 if (tc::elect_one()) {
@@ -487,50 +492,46 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc_raw(const WgradTcParams q) 
                 }
                 __syncwarp();
             }
+            ++ntile_done;
         }
-        if (tile == tile_beg) dbg_stamp(q.dbg, 3);
-        ++ntile_done;
     }
-    dbg_stamp(q.dbg, 4);
-    if (ntile_done > 0) ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1);
     tc::tc_fence_after();
     if (!ok) timeout_s = 1;
     __syncthreads();
     dbg_stamp(q.dbg, 5);
-    if (q.dbg && threadIdx.x == 64) {
-        dbg_put(1, 8, dbg_acc[0]); dbg_put(1, 9, dbg_acc[1]); dbg_put(1, 10, dbg_acc[2]);
-        for (int i = 0; i < 5; ++i) dbg_put(1, 11 + i, dbg_tile[i]);
-    }
 
-    // ---- epilogue (identical to k_wgrad_tc) ----
+    // ---- epilogue (workers; same layout as k_wgrad_tc) ----
     const int co = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* out = p.part + (size_t)blockIdx.x * p.part_stride;
     const int nblk = (q.Npad + 31) >> 5;
     const float poison = __int_as_float(0x7fc00000);
-    for (int j = 0; j < p.k; ++j)
-        for (int blk = warp >> 2; blk < nblk; blk += 2) {
-            float v[32];
-            if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
-            if (co >= q.TN) continue;
+    if (worker)
+        for (int j = 0; j < p.k; ++j)
+            for (int blk = warp >> 2; blk < nblk; blk += 2) {
+                float v[32];
+                if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
+                if (co >= q.TN) continue;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int ci = blk * 32 + i;
-                if (ci < p.Rows)
-                    out[((size_t)j * p.Rows + ci) * q.TN + co] = timeout_s ? poison : (ntile_done > 0 ? v[i] : 0.f);
+                for (int i = 0; i < 32; ++i) {
+                    const int ci = blk * 32 + i;
+                    if (ci < p.Rows)
+                        out[((size_t)j * p.Rows + ci) * q.TN + co] = timeout_s ? poison : (ntile_done > 0 ? v[i] : 0.f);
+                }
             }
-        }
     if (q.bias) {
         float* red = smem;
+        if (worker) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            float c4[4] = {bsum[u].x, bsum[u].y, bsum[u].z, bsum[u].w};
+            for (int u = 0; u < 8; ++u) {
+                float c4[4] = {bsum[u].x, bsum[u].y, bsum[u].z, bsum[u].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float sv = c4[e];
+                for (int e = 0; e < 4; ++e) {
+                    float sv = c4[e];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-                if (lane == 0) red[warp * 32 + u * 4 + e] = sv;
+                    for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                    if (lane == 0) red[warp * 32 + u * 4 + e] = sv;
+                }
             }
         }
         __syncthreads();
@@ -579,7 +580,7 @@ inline cudaError_t launch_wgrad_tc_raw_nx(const WgradTcParams& q, int nchunk, cu
     const size_t g = (size_t)16 * 129 * 4 * (SPLIT ? 2 : 1), x = (size_t)16 * tc::chunk_rows(q.Npad) * 4 * (SPLIT ? 2 : 1);
     const size_t smem = (g + q.nslot * x + wgrad_raw_floats(q.Npad, q.p.k, q.p.dil)) * sizeof(float);
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
-    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L>, dim3(nchunk), dim3(256), smem, s, q);
+    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L>, dim3(nchunk), dim3(288), smem, s, q);
     if (le != cudaSuccess) return le;
     return launch_check();
 }
