@@ -157,6 +157,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(family):
+    """DRAM bytes (read + write) of one launch of the family's kernel from the committed `ncu --set full`
+    capture (profiles/ncu_traffic_r1b.json; produced by profiles/call_ncu.sh on the same workload)."""
+    name = {"resblock_fwd": "k_resblock_fwd_tc", "conv": "k_conv_tc", "wgrad": "k_wgrad_tc_raw"}.get(family)
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r1b.json")
+    if name is None or not os.path.exists(p):
+        return None, None
+    k = json.load(open(p))["kernels"].get(name)
+    if not k:
+        return None, None
+    return k["dram_bytes_read"] + k["dram_bytes_write"], f"profiles/ncu_traffic_r1b.json: {k['kernel']}"
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -305,6 +318,7 @@ def run_b200(args, rank, local_rank, world):
         peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         vq = kern.get("vq_argmin", {})
         vq_gbs = (520.0 * F) / (vq["avg_us"] * 1e-6) / 1e9 if vq and vq.get("avg_us") else None
+        traffic, traffic_src = ncu_traffic(dom) if args.precision != "fp32" else (None, None)
         dense_ms = sum(v["ms_per_step"] for v in dense.values())
         dense_gf = sum(v["gflop_per_step"] for v in dense.values())
         line = {
@@ -330,7 +344,8 @@ def run_b200(args, rank, local_rank, world):
                            "conv": "k_conv_tc (dgrad / plain conv family)",
                            "wgrad": "k_wgrad_tc (weight-gradient family)"}[dom] if args.precision != "fp32" else dom,
                 "bound": "tensor", "achieved": ach, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": ach / peak_tf if (peak_tf and ach) else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / peak_tf if (peak_tf and ach) else None, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "all_dense_kernels": {"gflop_per_step": dense_gf, "ms_per_step": dense_ms,
                                       "tflops": dense_gf / dense_ms if dense_ms else None},
                 "peak_source": peaks_src + " bf16 sustained; kernel arithmetic: " + args.precision,
