@@ -218,6 +218,7 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keeps NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
         _dp.enable()
     kind = args.trainer
