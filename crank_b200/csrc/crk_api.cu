@@ -275,7 +275,9 @@ int crk_vq_stats(const float* x, int ldx, const long long* idx, float* counts, f
         API_TRY(cudaFuncSetAttribute(k_vq_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    k_vq_stats<<<nchunk, CRK_THREADS, (size_t)K * 65 * sizeof(float), (cudaStream_t)stream>>>(p);
+    const size_t stats_smem = ((size_t)K * 64 + (((size_t)K + 3) & ~(size_t)3) + 2 * 32 * 64) * sizeof(float);
+    if (stats_smem > 200 * 1024) return CRK_ERR_UNSUPPORTED;
+    k_vq_stats<<<nchunk, CRK_THREADS, stats_smem, (cudaStream_t)stream>>>(p);
     API_TRY(launch_check());
     k_vq_stats_reduce<<<cdiv(K * 65, 256), 256, 0, (cudaStream_t)stream>>>(ws, nchunk, K, counts, esum);
     API_TRY(launch_check());

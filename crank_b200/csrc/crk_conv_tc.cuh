@@ -32,8 +32,11 @@ struct ConvTcParams {
 };
 
 // A-tile staging of the gate-backward mode: 128 rows x 128 interleaved [sqrt(.5)*dH | dS] columns
-template <bool SPLIT, int U>
-__device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats, const ConvTcParams& q, int b, int t0) {
+// KEEP: the staged values stay in `keep` (one round: U * 256 == 128 * 32) and the GOS global store is issued
+// later by the caller, overlapped with the MMAs, instead of competing with the dH / dS loads here
+template <bool SPLIT, int U, bool KEEP>
+__device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats, const ConvTcParams& q, int b, int t0,
+                                             float4 (&keep)[KEEP ? U : 1]) {
     const ConvParams& p = q.p;
     const int total = CRK_TC_TM * 32;                      // (row, pair q): one float4 of A each
     for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
@@ -57,7 +60,8 @@ __device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats
             if (idx >= total) continue;
             const float4 v = make_float4(h[u].x * CRK_SQRT_HALF, h[u].y * CRK_SQRT_HALF, sg[u].x, sg[u].y);
             const int t = t0 + rr[u];
-            if (t < p.T) reinterpret_cast<float4*>(q.g_GOS + ((size_t)b * p.T + t) * 128)[qq[u]] = v;
+            if (KEEP) keep[KEEP ? u : 0] = v;
+            else if (t < p.T) reinterpret_cast<float4*>(q.g_GOS + ((size_t)b * p.T + t) * 128)[qq[u]] = v;
             const int off = qq[u] * cs_floats + rr[u] * 4;  // chunk = pair index (4 interleaved columns)
             if (SPLIT) {
                 float4 hh, ll;
@@ -218,7 +222,12 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     // the whole A tile in ONE batch of independent loads when the registers allow (3xTF32 variant: one CTA
     // per SM, 255 registers): a batch costs ~2.4K cycles however many loads it holds (measured: 5 batches
     // of 4 = 12K cycles for the K=128 dgrad tile)
-    if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, (SPLIT ? 16 : 4)>(Xh, Xl, csx, q, b, t0);
+    // gate mode, 3xTF32 variant (one CTA per SM, registers to spare): the staged [sqrt(.5) dH | dS] values stay in
+    // registers; their GOS store and the TaSb loads of the epilogue are issued while the MMAs run
+    constexpr bool GATE_OVERLAP = (MODE == CRK_CONV_GATE) && SPLIT;
+    float4 gkeep[GATE_OVERLAP ? 16 : 1];
+    float4 gts[GATE_OVERLAP ? 16 : 1];
+    if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, (SPLIT ? 16 : 4), GATE_OVERLAP>(Xh, Xl, csx, q, b, t0, gkeep);
     else if constexpr (MODE == CRK_CONV_FAST) tc_stage_act_pro<SPLIT, (SPLIT ? 9 : 5), false, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX, q.kshift);
     else tc_stage_act_pro<SPLIT, 4, true, false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
     tc::fence_proxy_async_smem();
@@ -263,6 +272,47 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
         if (lane == 0) dbg_put(q.dbg, 8, wfull);
         __syncwarp();
     }
+    // FAST mode: side inputs of the epilogue (residual gradient, dropout multiplier, activation-derivative
+    // source, old output) -- U float4 each.  Fetching the first round here, under the MMAs, was measured SLOWER
+    // (conv family 7.2 -> 7.7 ms per step: the loads contend with the weight stream and lengthen the MMA
+    // phase by more than the epilogue saves), unlike the gate mode's TaSb prefetch below; kept switchable.
+    constexpr bool EPI_PRE = false;
+    constexpr int EU = (MODE == CRK_CONV_FAST) ? (SPLIT ? 8 : 4) : 1;
+    float4 mulv[EU], rv[EU], dv[EU], oldv[EU];
+    auto epi_side_load = [&](int e0) {
+        const int c4n = p.Cout >> 2;
+        const int total = min(CRK_TC_TM, p.T - t0) * c4n;
+        const size_t row0 = (size_t)b * p.T + t0;
+        const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+            const int e = e0 + u * blockDim.x;
+            mulv[u] = one4; rv[u] = zero4; dv[u] = one4; oldv[u] = zero4;
+            if (e < total) {
+                const int rr = e >> q.nshift, c4 = e - rr * c4n;
+                const size_t row = row0 + rr;
+                if (p.mul_src) mulv[u] = __ldg(reinterpret_cast<const float4*>(p.mul_src + row * p.ldmul) + c4);
+                if (p.R) rv[u] = __ldg(reinterpret_cast<const float4*>(p.R + row * p.ldr) + c4);
+                if (p.dact_src) dv[u] = __ldg(reinterpret_cast<const float4*>(p.dact_src + row * p.lddact) + c4);
+                if (p.accumulate) oldv[u] = *(reinterpret_cast<const float4*>(p.Y + row * p.ldy) + c4);
+            }
+        }
+    };
+    if constexpr (EPI_PRE) epi_side_load(threadIdx.x);
+    if constexpr (GATE_OVERLAP) {
+        const size_t row0g = (size_t)b * p.T + t0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = threadIdx.x + u * 256, rr = e >> 5, qi = e & 31;
+            if (t0 + rr < p.T) reinterpret_cast<float4*>(q.g_GOS + (row0g + rr) * 128)[qi] = gkeep[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = threadIdx.x + u * 256, rr = e >> 5, qi = e & 31;
+            gts[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t0 + rr < p.T) gts[u] = __ldg(reinterpret_cast<const float4*>(q.g_TaSb + (row0g + rr) * 128) + qi);
+        }
+    }
     ok &= tc::mbar_wait(&bar_acc, 0);
     tc::tc_fence_after();
     if (!ok) timeout_s = 1;
@@ -287,7 +337,23 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     }
     __syncthreads();
     dbg_stamp(q.dbg, 3);
-    if constexpr (MODE == CRK_CONV_GATE) {
+    if constexpr (GATE_OVERLAP) {
+        const size_t row0 = (size_t)b * p.T + t0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int e = threadIdx.x + u * 256, rr = e >> 5, qi = e & 31;
+            if (t0 + rr >= p.T) continue;
+            const float4 ts = gts[u];
+            const float dz0 = S[rr * sst + 2 * qi], dz1 = S[rr * sst + 2 * qi + 1];
+            float4 dg;                                  // same expressions as the non-overlapped path below
+            dg.x = (dz0 * ts.z) * (1.f - ts.x * ts.x);
+            dg.y = (dz1 * ts.w) * (1.f - ts.y * ts.y);
+            dg.z = (dz0 * ts.x) * ((1.f - ts.z) * ts.z);
+            dg.w = (dz1 * ts.y) * ((1.f - ts.w) * ts.w);
+            reinterpret_cast<float4*>(q.g_DG + (row0 + rr) * 128)[qi] = dg;
+            reinterpret_cast<float2*>(q.g_Z + (row0 + rr) * 64)[qi] = make_float2(ts.x * ts.z, ts.y * ts.w);
+        }
+    } else if constexpr (MODE == CRK_CONV_GATE) {
         // lanes over gate pairs (2 z channels each): TaSb read and DG write are one float4 per lane
         const int nlive = min(CRK_TC_TM, p.T - t0);
         const size_t row0 = (size_t)b * p.T + t0;
@@ -324,22 +390,9 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
         const int c4n = p.Cout >> 2;
         const int total = nlive * c4n;
         constexpr int U = SPLIT ? 8 : 4;                    // (the 2-CTA/SM plain-TF32 variant is capped at 128 registers)
-        const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * U) {
-            float4 mulv[U], rv[U], dv[U], oldv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = e0 + u * blockDim.x;
-                mulv[u] = one4; rv[u] = zero4; dv[u] = one4; oldv[u] = zero4;
-                if (e < total) {
-                    const int rr = e >> q.nshift, c4 = e - rr * c4n;
-                    const size_t row = row0 + rr;
-                    if (p.mul_src) mulv[u] = __ldg(reinterpret_cast<const float4*>(p.mul_src + row * p.ldmul) + c4);
-                    if (p.R) rv[u] = __ldg(reinterpret_cast<const float4*>(p.R + row * p.ldr) + c4);
-                    if (p.dact_src) dv[u] = __ldg(reinterpret_cast<const float4*>(p.dact_src + row * p.lddact) + c4);
-                    if (p.accumulate) oldv[u] = *(reinterpret_cast<const float4*>(p.Y + row * p.ldy) + c4);
-                }
-            }
+            // round 0 of the 3xTF32 variant was loaded while the MMAs ran (epi_side_load before the accumulator wait)
+            if (!(EPI_PRE && e0 == (int)threadIdx.x)) epi_side_load(e0);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = e0 + u * blockDim.x;
@@ -439,7 +492,7 @@ inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
     TimedLaunch tl(MODE == CRK_CONV_GATE ? CRK_K_BWD_GATE : CRK_K_CONV, s,
                    MODE == CRK_CONV_GATE ? 2.0 * q.p.B * q.p.T * 128.0 * 64 : 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.Cout * q.p.k);
     ConvTcParams qq = q;
-    qq.dbg = MODE == CRK_CONV_GATE ? 0 : dbg_take(CRK_K_CONV);
+    qq.dbg = dbg_take(MODE == CRK_CONV_GATE ? CRK_K_BWD_GATE : CRK_K_CONV);
     cudaError_t le = launch_pdl(k_conv_tc<SPLIT, MODE>, dim3(tiles), dim3(256), conv_tc_smem(q, SPLIT), s, qq);
     if (le != cudaSuccess) return le;
     return launch_check();

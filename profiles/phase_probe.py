@@ -26,6 +26,7 @@ for _ in range(2):
 # then per layer dgrad...; wgrad TC: head(0,1) then per layer: Wos(2), conv(3), ...
 sel = {"resblock_fwd k5 d2": (1, 3, ["stageX", "gemm1+TMA", "epi1", "gemm2+TaSb", "epi2"], 6),
        "conv dgrad k5 (K128,N64)": (3, 5, ["stageA", "mma+TMA", "tmem->smem", "coalesced epilogue"], 5),
+       "gate backward (K128,N64,k1)": (4, 3, ["stage dH,dS->GOS", "mma+TMA", "tmem->smem", "gate' epilogue"], 5),
        "wgrad conv k5": (2, 3, ["issue loads+wait", "store G,X0", "taps(tile0)", "other tiles", "wait last", "epilogue"], 7),
        "wgrad out|skip k1 (N=128 G cols, Cin 64)": (2, 2, ["issue loads+wait", "store G,X0", "taps(tile0)", "other tiles", "wait last", "epilogue"], 7)}
 for name, (kid, idx, labels, n) in sel.items():
@@ -40,6 +41,7 @@ for name, (kid, idx, labels, n) in sel.items():
     diag = {"resblock_fwd k5 d2": ["issuer wait for weights"],
             "conv dgrad k5 (K128,N64)": ["issuer wait for weights", "producer wait for free slot"],
             "wgrad out|skip k1 (N=128 G cols, Cin 64)": [],
+            "gate backward (K128,N64,k1)": ["issuer wait for weights", "producer wait for free slot"],
             "wgrad conv k5": ["slot waits", "transposition", "barrier", "tile: wait prev MMAs", "tile: G store", "tile: raw store",
                               "tile: issue next loads", "tile: barrier"]}[name]
     print("   diag (cycles, CTA mean):", {l: int(full[:, 8 + i].mean()) for i, l in enumerate(diag)})
