@@ -81,6 +81,48 @@ __device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats
 // costs instruction-cache footprint)
 // c4shift >= 0: Kpad / 4 is a power of two (index split by shift: the runtime division is ~30 instructions per
 // element in code that runs once per CTA)
+// 128-bit version for the overlapped gate mode: one item = (row, 4 consecutive z channels) = TWO gate pairs, so dH
+// and dS are read with 16 B loads (8 + 8 per thread instead of 16 + 16 of 8 B); the staged values stay in
+// `keep` (the caller stores them to GOS under the MMAs).  Exactly one round: 8 * 256 == 128 rows * 16.
+template <bool SPLIT>
+__device__ __forceinline__ void tc_stage_gos4(float* hi, float* lo, int cs_floats, const ConvTcParams& q, int b, int t0,
+                                              float4 (&keep)[16]) {
+    const ConvParams& p = q.p;
+    float4 h[8], sg[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int idx = threadIdx.x + u * 256, rr = idx >> 4, pp = idx & 15;
+        h[u] = make_float4(0.f, 0.f, 0.f, 0.f); sg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t0 + rr < p.T) {
+            const size_t row = (size_t)b * p.T + t0 + rr;
+            if (q.g_dH) h[u] = __ldg(reinterpret_cast<const float4*>(q.g_dH + row * 64) + pp);
+            sg[u] = __ldg(reinterpret_cast<const float4*>(q.g_dS + row * 64) + pp);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int idx = threadIdx.x + u * 256, rr = idx >> 4, pp = idx & 15;
+        const float4 v0 = make_float4(h[u].x * CRK_SQRT_HALF, h[u].y * CRK_SQRT_HALF, sg[u].x, sg[u].y);
+        const float4 v1 = make_float4(h[u].z * CRK_SQRT_HALF, h[u].w * CRK_SQRT_HALF, sg[u].z, sg[u].w);
+        keep[2 * u] = v0; keep[2 * u + 1] = v1;
+        const int off = (2 * pp) * cs_floats + rr * 4;          // chunk = pair index
+        if (SPLIT) {
+            float4 hh, ll;
+            tc::split_tf32(v0.x, hh.x, ll.x); tc::split_tf32(v0.y, hh.y, ll.y);
+            tc::split_tf32(v0.z, hh.z, ll.z); tc::split_tf32(v0.w, hh.w, ll.w);
+            *reinterpret_cast<float4*>(hi + off) = hh;
+            *reinterpret_cast<float4*>(lo + off) = ll;
+            tc::split_tf32(v1.x, hh.x, ll.x); tc::split_tf32(v1.y, hh.y, ll.y);
+            tc::split_tf32(v1.z, hh.z, ll.z); tc::split_tf32(v1.w, hh.w, ll.w);
+            *reinterpret_cast<float4*>(hi + off + cs_floats) = hh;
+            *reinterpret_cast<float4*>(lo + off + cs_floats) = ll;
+        } else {
+            *reinterpret_cast<float4*>(hi + off) = v0;
+            *reinterpret_cast<float4*>(hi + off + cs_floats) = v1;
+        }
+    }
+}
+
 template <bool SPLIT, int U, bool HASMUL, bool VECONLY>
 __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_floats, const ConvParams& p, int Kpad,
                                                  int b, int tstart, int rows, int c4shift = -1) {
@@ -227,7 +269,8 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     constexpr bool GATE_OVERLAP = (MODE == CRK_CONV_GATE) && SPLIT;
     float4 gkeep[GATE_OVERLAP ? 16 : 1];
     float4 gts[GATE_OVERLAP ? 16 : 1];
-    if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, (SPLIT ? 16 : 4), GATE_OVERLAP>(Xh, Xl, csx, q, b, t0, gkeep);
+    if constexpr (GATE_OVERLAP) tc_stage_gos4<SPLIT>(Xh, Xl, csx, q, b, t0, gkeep);
+    else if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, 4, false>(Xh, Xl, csx, q, b, t0, gkeep);
     else if constexpr (MODE == CRK_CONV_FAST) tc_stage_act_pro<SPLIT, (SPLIT ? 9 : 5), false, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX, q.kshift);
     else tc_stage_act_pro<SPLIT, 4, true, false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
     tc::fence_proxy_async_smem();
@@ -302,9 +345,12 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     if constexpr (GATE_OVERLAP) {
         const size_t row0g = (size_t)b * p.T + t0;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int e = threadIdx.x + u * 256, rr = e >> 5, qi = e & 31;
-            if (t0 + rr < p.T) reinterpret_cast<float4*>(q.g_GOS + (row0g + rr) * 128)[qi] = gkeep[u];
+        for (int u = 0; u < 8; ++u) {                       // same (row, channel quad) items as tc_stage_gos4
+            const int idx = threadIdx.x + u * 256, rr = idx >> 4, pp = idx & 15;
+            if (t0 + rr < p.T) {
+                float4* dst = reinterpret_cast<float4*>(q.g_GOS + (row0g + rr) * 128) + 2 * pp;
+                dst[0] = gkeep[2 * u]; dst[1] = gkeep[2 * u + 1];
+            }
         }
 #pragma unroll
         for (int u = 0; u < 16; ++u) {

@@ -322,7 +322,8 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
     WavenetLayout L;
     int rc = wavenet_layout(c, &L);
     if (rc) return rc;
-    if (!theta || !weff || !x || !act || !dy || !gtheta || !ws || B < 1 || T < 1) return CRK_ERR_ARG;
+    if (!theta || !weff || !x || !act || !dy || !ws || B < 1 || T < 1) return CRK_ERR_ARG;
+    const bool need_w = gtheta != nullptr;    // NULL: input gradients only (frozen parameters): every wgrad is skipped
     const long long F = (long long)B * T;
     const WavenetAct A = wavenet_act(c, F);
     const WavenetWs W = wavenet_ws(c, L, B, T);
@@ -341,7 +342,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
         g.X = head1; g.ldx = 64; g.Cin = 64; g.Rows = 64;
         g.pro_act = c->head_act; g.pro_slope = c->slope; g.pro_scale = 1.f; g.xmul = nullptr; g.ldxmul = 0;
         g.G = dy; g.ldg = lddy; g.N = c->out_ch; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-        CRK_TRY(conv_wgrad(g, cpt_out, gweff + d.w_off, gweff + d.bias_off, part, s));
+        if (need_w) CRK_TRY(conv_wgrad(g, cpt_out, gweff + d.w_off, gweff + d.bias_off, part, s));
         ConvParams p = conv_params_default();   // dhead1 = (dy . W2^T) * act'(head1)
         p.X = dy; p.ldx = lddy; p.Cin = c->out_ch; p.CinPad = d.wt_rows;
         p.W = weff + d.wt_off; p.Y = ws + W.dhead1; p.ldy = 64; p.Cout = 64; p.B = B; p.T = T;
@@ -354,7 +355,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
         g.X = skips; g.ldx = 64; g.Cin = 64; g.Rows = 64;
         g.pro_act = c->head_act; g.pro_slope = c->slope; g.pro_scale = hscale; g.xmul = nullptr; g.ldxmul = 0;
         g.G = ws + W.dhead1; g.ldg = 64; g.N = 64; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-        CRK_TRY(conv_wgrad(g, 2, gweff + d.w_off, gweff + d.bias_off, part, s));
+        if (need_w) CRK_TRY(conv_wgrad(g, 2, gweff + d.w_off, gweff + d.bias_off, part, s));
         ConvParams p = conv_params_default();   // ds = (dhead1 . W1^T) * act'(skips) * hscale
         p.X = ws + W.dhead1; p.ldx = 64; p.Cin = 64; p.CinPad = 64;
         p.W = weff + d.wt_off; p.Y = ws + W.ds; p.ldy = 64; p.Cout = 64; p.B = B; p.T = T;
@@ -386,7 +387,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
             g.X = ws + W.z; g.ldx = 64; g.Cin = 64; g.Rows = 64;
             g.pro_act = CRK_ACT_NONE; g.pro_slope = 0.f; g.pro_scale = 1.f; g.xmul = nullptr; g.ldxmul = 0;
             g.G = ws + W.gos; g.ldg = 128; g.N = 128; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-            CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, gweff + d.bias_off, part, s));
+            if (need_w) CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, gweff + d.bias_off, part, s));
         }
         {   // dilated conv weights
             const crk_conv_desc& d = L.tab.d[L.conv[l]];
@@ -395,7 +396,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
             g.pro_act = CRK_ACT_NONE; g.pro_slope = 0.f; g.pro_scale = 1.f; g.xmul = dm; g.ldxmul = 64;
             g.G = ws + W.dg; g.ldg = 128; g.N = 128; g.B = B; g.T = T;
             g.k = c->kernel_size; g.dil = dil; g.padl = padl;
-            CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, gweff + d.bias_off, part, s));
+            if (need_w) CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, gweff + d.bias_off, part, s));
         }
         if (c->aux_ch > 0) {
             const crk_conv_desc& d = L.tab.d[L.aux[l]];
@@ -403,7 +404,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
             g.X = cond; g.ldx = ldc; g.Cin = c->aux_ch; g.Rows = d.cin_pad;
             g.pro_act = CRK_ACT_NONE; g.pro_slope = 0.f; g.pro_scale = 1.f; g.xmul = nullptr; g.ldxmul = 0;
             g.G = ws + W.dg; g.ldg = 128; g.N = 128; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-            CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, nullptr, part, s));
+            if (need_w) CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, nullptr, part, s));
             if (dc) {
                 ConvParams p = conv_params_default();
                 p.X = ws + W.dg; p.ldx = 128; p.Cin = 128; p.CinPad = 128;
@@ -436,7 +437,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
         g.X = x; g.ldx = ldx; g.Cin = c->in_ch; g.Rows = d.cin_pad;
         g.pro_act = CRK_ACT_NONE; g.pro_slope = 0.f; g.pro_scale = 1.f; g.xmul = nullptr; g.ldxmul = 0;
         g.G = dh_cur; g.ldg = 64; g.N = 64; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-        CRK_TRY(conv_wgrad(g, 2, gweff + d.w_off, gweff + d.bias_off, part, s));
+        if (need_w) CRK_TRY(conv_wgrad(g, 2, gweff + d.w_off, gweff + d.bias_off, part, s));
         if (dx) {
             ConvParams p = conv_params_default();
             p.X = dh_cur; p.ldx = 64; p.Cin = 64; p.CinPad = 64;
@@ -444,7 +445,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
             CRK_TRY(conv_dispatch(p, cpt_for(c->in_ch), weff + d.tct_off, d.tct_kpad, d.tct_n, s));
         }
     }
-    CRK_TRY(launch_weightnorm_bwd(L.tab, theta, gweff, gtheta, s));
+    if (need_w) CRK_TRY(launch_weightnorm_bwd(L.tab, theta, gweff, gtheta, s));
     return CRK_OK;
 }
 
@@ -542,7 +543,8 @@ inline int convstack_bwd(const crk_convstack_cfg* c, const float* theta, const f
     ConvstackLayout L;
     int rc = convstack_layout(c, &L);
     if (rc) return rc;
-    if (!theta || !weff || !x || !act || !dy || !gtheta || !ws || B < 1 || T < 1) return CRK_ERR_ARG;
+    if (!theta || !weff || !x || !act || !dy || !ws || B < 1 || T < 1) return CRK_ERR_ARG;
+    const bool need_w = gtheta != nullptr;    // NULL: input gradients only (frozen parameters)
     const long long F = (long long)B * T;
     const ConvstackWs W = convstack_ws(c, L, B, T);
     float* gweff = ws + W.gweff;
@@ -562,7 +564,7 @@ inline int convstack_bwd(const crk_convstack_cfg* c, const float* theta, const f
         g.X = xin; g.ldx = ldxin; g.Cin = L.cin[i]; g.Rows = d.cin_pad;
         g.pro_act = CRK_ACT_NONE; g.pro_slope = 0.f; g.pro_scale = 1.f; g.xmul = nullptr; g.ldxmul = 0;
         g.G = dcur; g.ldg = lddcur; g.N = L.cout[i]; g.B = B; g.T = T; g.k = c->kernel_size; g.dil = dil; g.padl = padl;
-        CRK_TRY(conv_wgrad(g, cpt_for(L.cout[i]), gweff + d.w_off, gweff + d.bias_off, part, s));
+        if (need_w) CRK_TRY(conv_wgrad(g, cpt_for(L.cout[i]), gweff + d.w_off, gweff + d.bias_off, part, s));
         if (i > 0 || dx) {
             ConvParams p = conv_params_default();
             p.X = dcur; p.ldx = lddcur; p.Cin = L.cout[i]; p.CinPad = d.wt_rows;
@@ -580,7 +582,7 @@ inline int convstack_bwd(const crk_convstack_cfg* c, const float* theta, const f
             flip ^= 1;
         }
     }
-    CRK_TRY(launch_weightnorm_bwd(L.tab, theta, gweff, gtheta, s));
+    if (need_w) CRK_TRY(launch_weightnorm_bwd(L.tab, theta, gweff, gtheta, s));
     return CRK_OK;
 }
 

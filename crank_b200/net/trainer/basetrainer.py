@@ -260,5 +260,24 @@ class BaseTrainer(object):
         return None
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def frozen(*modules):
+    """Run forwards whose PARAMETER gradients nobody reads (the discriminator / classifiers evaluated inside the
+    generator update: the reference accumulates those gradients and discards them at the module's next
+    zero_grad, crank/net/trainer/trainer_lsgan.py:146-160) without building them: the backward of such a
+    forward only propagates input gradients, i.e. skips every weight-gradient kernel."""
+    ps = [p for m in modules for p in m.parameters() if p.requires_grad]
+    for p in ps:
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p in ps:
+            p.requires_grad_(True)
+
+
 def pick_cv_speakers(spkrs, n):
     return random.sample(list(spkrs.keys()), n)

@@ -7,6 +7,7 @@ import random
 import torch
 
 from ... import ops
+from .basetrainer import frozen
 from .trainer_lsgan import LSGANTrainer
 
 
@@ -34,7 +35,8 @@ class CycleGANTrainer(LSGANTrainer):
         for c in range(self.conf["n_cycles"]):
             for io in ["org", "cv"]:
                 lbl = f"{c}cyc_{io}"
-                D_out = self._discriminate(self.get_D_inputs(batch, outputs[c][io]["decoded"], label="cv"))
+                with frozen(self.model["D"]):
+                    D_out = self._discriminate(self.get_D_inputs(batch, outputs[c][io]["decoded"], label="cv"))
                 if self.conf["acgan_flag"]:
                     D_out, spkr_cls = torch.split(D_out, [1, self.n_spkrs], dim=2)
                     loss[f"D_acgan_adv_{lbl}"] = self.criterion["ce"](

@@ -11,6 +11,7 @@ import torch
 
 from ... import ops
 from .. import _dp
+from .basetrainer import frozen
 from .trainer_vqvae import VQVAETrainer
 
 
@@ -96,7 +97,8 @@ class LSGANTrainer(VQVAETrainer):
         return loss
 
     def calculate_adv_loss(self, batch, decoded, h, mask, loss):
-        fake = self._discriminate(self.get_D_inputs(batch, decoded, label="cv"))
+        with frozen(self.model["D"]):       # generator update: only the gradient w.r.t. the decoded features is used
+            fake = self._discriminate(self.get_D_inputs(batch, decoded, label="cv"))
         if self.conf["acgan_flag"]:
             fake, spkr_cls = torch.split(fake, [1, self.n_spkrs], dim=2)
             loss = self.calculate_acgan_loss(spkr_cls, h, loss)

@@ -11,7 +11,7 @@ import torch
 
 from ... import ops
 from .. import _dp
-from .basetrainer import BaseTrainer, pick_cv_speakers
+from .basetrainer import BaseTrainer, frozen, pick_cv_speakers
 
 
 class VQVAETrainer(BaseTrainer):
@@ -170,7 +170,8 @@ class VQVAETrainer(BaseTrainer):
                 o = outputs[c][io]
                 if io == "cv":
                     emask = batch["encoder_mask"]
-                    fake = self._classify(o["decoded"])
+                    with frozen(self.model["C"]):       # part of the generator loss: classifier gradients are not used
+                        fake = self._classify(o["decoded"])
                     loss[f"C_fake_{lbl}"] = self.criterion["ce"](
                         fake.reshape(-1, fake.size(2)), batch["cv_h"].reshape(-1))
                 else:
@@ -184,7 +185,8 @@ class VQVAETrainer(BaseTrainer):
 
     def calculate_spkradv_loss(self, batch, outputs, loss, label="org", phase="train"):
         encoded, er = self._encoder_outputs(outputs)
-        logits = self.model["SPKRADV"].forward(encoded)
+        with frozen(self.model["SPKRADV"]):         # generator loss: only the (reversed) encoder gradient is used
+            logits = self.model["SPKRADV"].forward(encoded)
         loss[f"G_spkradv_{label}"] = self.criterion["ce"](
             logits.reshape(-1, logits.size(2)), batch["org_h"][:, er:].reshape(-1))
         w = self.conf["alpha"]["ce"]

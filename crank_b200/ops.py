@@ -75,7 +75,9 @@ class WavenetFn(torch.autograd.Function):
         need_dc = ctx.has_c and ctx.needs_input_grad[2]
         dx = torch.empty(B, T, cfg.in_ch, dtype=_f32, device=x.device) if need_dx else None
         dc = torch.empty(B, T, cfg.aux_ch, dtype=_f32, device=x.device) if need_dc else None
-        gtheta = torch.empty_like(theta)
+        # parameters frozen at forward time (e.g. the discriminator inside the generator update): input
+        # gradients only -- the library skips every weight-gradient kernel when gtheta is NULL
+        gtheta = torch.empty_like(theta) if ctx.needs_input_grad[4] else None
         ws = _empty(L.lib().crk_wavenet_ws_floats(C.byref(cfg), B, T), x.device)
         L.call("crk_wavenet_bwd", C.byref(cfg), L.ptr(theta), L.ptr(weff), L.ptr(x), ldx,
                L.ptr(c), ldc, L.ptr(dropmul), L.ptr(act), L.ptr(dy), lddy,
@@ -111,7 +113,7 @@ class ConvstackFn(torch.autograd.Function):
         dy, lddy = panel(dy)
         need_dx = ctx.needs_input_grad[1]
         dx = torch.empty(B, T, cfg.in_ch, dtype=_f32, device=x.device) if need_dx else None
-        gtheta = torch.empty_like(theta)
+        gtheta = torch.empty_like(theta) if ctx.needs_input_grad[2] else None
         ws = _empty(L.lib().crk_convstack_ws_floats(C.byref(cfg), B, T), x.device)
         L.call("crk_convstack_bwd", C.byref(cfg), L.ptr(theta), L.ptr(weff), L.ptr(x), ldx,
                L.ptr(act), L.ptr(dy), lddy, L.ptr(dx), cfg.in_ch, C.c_float(ctx.dx_scale),

@@ -124,7 +124,8 @@ int crk_wavenet_fwd(const crk_wavenet_cfg* cfg, const float* weff, const float* 
                     const float* c, int ldc, const float* dropmul, float* y, int ldy, float* act,
                     int B, int T, void* stream);
 
-/* backward.  dy (B*T,out_ch) ld lddy -> gtheta (same layout as theta, overwritten),
+/* backward.  dy (B*T,out_ch) ld lddy -> gtheta (same layout as theta, overwritten; NULL = parameters
+ * frozen: only input gradients are computed and every weight-gradient kernel is skipped),
  * dx (B*T,in_ch) ld lddx or NULL, dc (B*T,aux_ch) ld lddc or NULL (overwritten).
  * ws: scratch of crk_wavenet_ws_floats() floats. */
 int crk_wavenet_bwd(const crk_wavenet_cfg* cfg, const float* theta, const float* weff,
@@ -148,7 +149,8 @@ long long crk_convstack_ws_floats(const crk_convstack_cfg* cfg, int B, int T);
 int crk_convstack_weights(const crk_convstack_cfg* cfg, const float* theta, float* weff, void* stream);
 int crk_convstack_fwd(const crk_convstack_cfg* cfg, const float* weff, const float* x, int ldx,
                       float* y, int ldy, float* act, int B, int T, void* stream);
-/* dx_scale multiplies dx (gradient-reversal layer of crank/net/module/spkradv.py:63-72: -lambda) */
+/* dx_scale multiplies dx (gradient-reversal layer of crank/net/module/spkradv.py:63-72: -lambda);
+ * gtheta may be NULL (frozen parameters: input gradient only) */
 int crk_convstack_bwd(const crk_convstack_cfg* cfg, const float* theta, const float* weff,
                       const float* x, int ldx, const float* act, const float* dy, int lddy,
                       float* dx, int lddx, float dx_scale, float* gtheta, float* ws, int B, int T,

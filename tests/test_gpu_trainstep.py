@@ -181,3 +181,35 @@ def test_weight_cache_is_invalidated_by_fused_adam():
     opt.step()
     y1 = net(x)
     assert (y1 - y0).abs().max().item() > 1e-4, "forward after an optimizer step still used stale packed weights"
+
+
+def test_frozen_forward_skips_weight_gradients_but_keeps_input_gradient():
+    """`frozen(D)` (used for the discriminator inside the generator update) must leave dx bit-identical and
+    produce no parameter gradient (the C ABI gets gtheta = NULL and launches no wgrad kernel)."""
+    from crank_b200 import lib as L
+    from crank_b200.net.trainer.basetrainer import frozen
+    from crank_b200.parallel_wavegan.models import ResidualParallelWaveGANDiscriminator
+
+    torch.manual_seed(5)
+    D = ResidualParallelWaveGANDiscriminator(in_channels=113, out_channels=1, kernel_size=5, layers=8, stacks=4,
+                                             dropout=0.0).cuda()
+    x = torch.randn(3, 200, 113, device="cuda")
+    dy = torch.randn(3, 200, 1, device="cuda")
+    xa = x.clone().requires_grad_(True)
+    D.forward_cl(xa).backward(dy)
+    g_full = D.theta.grad.clone()
+    D.zero_grad(set_to_none=True)
+    xb = x.clone().requires_grad_(True)
+    n0 = L.lib().crk_launch_count()
+    with frozen(D):
+        y = D.forward_cl(xb)
+    assert D.theta.requires_grad
+    y.backward(dy)
+    n_frozen = L.lib().crk_launch_count() - n0
+    assert D.theta.grad is None
+    assert torch.equal(xa.grad, xb.grad)
+    assert g_full.abs().max() > 0
+    xc = x.clone().requires_grad_(True)
+    n1 = L.lib().crk_launch_count()
+    D.forward_cl(xc).backward(dy)
+    assert n_frozen < L.lib().crk_launch_count() - n1      # fewer kernels: no wgrad / reduce / weight-norm backward
