@@ -153,6 +153,11 @@ int crk_wavenet_fwd(const crk_wavenet_cfg* cfg, const float* weff, const float* 
                     int B, int T, void* stream) {
     return wavenet_fwd(cfg, weff, x, ldx, c, ldc, dropmul, y, ldy, act, B, T, (cudaStream_t)stream);
 }
+int crk_wavenet_infer(const crk_wavenet_cfg* cfg, const float* weff, const float* x, int ldx,
+                      const float* c, int ldc, const float* dropmul, float* y, int ldy, float* act,
+                      int B, int T, void* stream) {
+    return wavenet_fwd(cfg, weff, x, ldx, c, ldc, dropmul, y, ldy, act, B, T, (cudaStream_t)stream, false);
+}
 int crk_wavenet_bwd(const crk_wavenet_cfg* cfg, const float* theta, const float* weff,
                     const float* x, int ldx, const float* c, int ldc, const float* dropmul,
                     const float* act, const float* dy, int lddy, float* dx, int lddx, float* dc,

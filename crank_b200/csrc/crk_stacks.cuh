@@ -243,9 +243,11 @@ inline WavenetWs wavenet_ws(const crk_wavenet_cfg* c, const WavenetLayout& L, in
     return w;
 }
 
+// save_gates = false: inference / no-grad forward -- the (tanh, sigmoid) pairs backward would need are not
+// written (512 B per frame and layer, 40% of the fused block's output traffic)
 inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float* x, int ldx,
                        const float* cond, int ldc, const float* dropmul, float* y, int ldy, float* act,
-                       int B, int T, cudaStream_t s) {
+                       int B, int T, cudaStream_t s, bool save_gates = true) {
     WavenetLayout L;
     int rc = wavenet_layout(c, &L);
     if (rc) return rc;
@@ -277,7 +279,7 @@ inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float*
         } else { p.Caux = nullptr; p.ldc = 0; p.Ca = 0; p.CaPad = 0; p.Wa = nullptr; }
         p.Wos = weff + L.tab.d[L.out[l]].w_off; p.bos = weff + L.tab.d[L.out[l]].bias_off;
         p.dropmul = dropmul ? dropmul + (long long)l * F * 64 : nullptr;
-        p.TaSb = act + A.tasb + (long long)l * F * 128;
+        p.TaSb = save_gates ? act + A.tasb + (long long)l * F * 128 : nullptr;
         p.B = B; p.T = T; p.k = c->kernel_size; p.dil = dil; p.padl = wn_padl(c, dil);
         const int mode = precision_mode();
         if (mode == CRK_PREC_FP32 || (tc_disable_mask() & 1) || (c->kernel_size - 1) * dil > 16) {

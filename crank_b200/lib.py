@@ -68,6 +68,7 @@ SIGNATURES = {
     "crk_wavenet_ws_floats": (i64, [PW, i32, i32]),
     "crk_wavenet_weights": (i32, [PW, vp, vp, vp]),
     "crk_wavenet_fwd": (i32, [PW, vp, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, vp]),
+    "crk_wavenet_infer": (i32, [PW, vp, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, vp]),
     "crk_wavenet_bwd": (i32, [PW, vp, vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, vp]),
     "crk_convstack_describe": (i32, [PC, PD, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
     "crk_convstack_act_floats": (i64, [PC, i32, i32]),

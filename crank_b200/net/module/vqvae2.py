@@ -54,12 +54,17 @@ class VQVAE2(nn.Module):
             return self.preprocess_layer(x)
         return x
 
-    def forward(self, x, enc_h, dec_h, spkrvec=None, use_ema=True, encoder_detach=False):
+    def forward(self, x, enc_h, dec_h, spkrvec=None, use_ema=True, encoder_detach=False, final_decoder=True):
+        """`final_decoder=False` (not in the reference signature; default = reference behaviour) skips the bottom
+        decoder stack, whose output no quantiser consumes: used by the speaker-adversarial update, which only reads
+        the encoder outputs of this pass but must keep its EMA codebook updates (trainer_vqvae.py:165-180).
+        "decoded" is then None."""
         x = self._pre(x)
         dec_h = self._get_dec_h(dec_h, spkrvec)
         enc = self.encode(x, enc_h=enc_h)
         enc_unmod = list(enc)
-        enc, dec, emb_idxs, _, qidxs = self.decode(enc, dec_h, use_ema=use_ema, detach=encoder_detach)
+        enc, dec, emb_idxs, _, qidxs = self.decode(enc, dec_h, use_ema=use_ema, detach=encoder_detach,
+                                                   final_decoder=final_decoder)
         return self.make_dict(enc, dec, emb_idxs, qidxs, enc_unmod)
 
     def cycle_forward(self, x, org_enc_h, org_dec_h, cv_enc_h, cv_dec_h, org_spkrvec, cv_spkrvec):
@@ -97,7 +102,7 @@ class VQVAE2(nn.Module):
             encoded.append(enc)
         return encoded
 
-    def decode(self, enc, dec_h, use_ema=True, detach=False):
+    def decode(self, enc, dec_h, use_ema=True, detach=False, final_decoder=True):
         dec = None
         emb_idxs, emb_idx_qxs, qidxs = [], [], []
         for n in reversed(range(self.conf["n_vq_stacks"])):
@@ -111,8 +116,10 @@ class VQVAE2(nn.Module):
             qidxs.append(qidx)
             if n != 0:
                 dec = self.decoders[n].forward_cl(qx, None)
-            else:
+            elif final_decoder:
                 dec = self.decoders[n].forward_cl(torch.cat(emb_idx_qxs, dim=-1), dec_h)
+            else:
+                dec = None
         return enc, dec, emb_idxs, emb_idx_qxs, qidxs
 
     def remove_weight_norm(self):

@@ -24,7 +24,8 @@ class CycleGANTrainer(LSGANTrainer):
         return loss
 
     def update_D(self, batch, loss, phase="train"):
-        outputs = self._cycle(batch)
+        with torch.no_grad():       # every use below is .detach()-ed
+            outputs = self._cycle(batch)
         loss = self.calculate_cycle_discriminator_loss(batch, outputs, loss)
         if phase == "train":
             self.step_model(loss, model="D")

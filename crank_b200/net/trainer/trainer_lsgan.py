@@ -87,7 +87,8 @@ class LSGANTrainer(VQVAETrainer):
         else:
             dec_h, spkrvec = self._get_dec_h(batch)
             h = batch["org_h"]
-        outputs = self.model["G"].forward(batch["in_feats"], enc_h, dec_h, spkrvec)
+        with torch.no_grad():       # only decoded.detach() is used below: no autograd graph, no saved activations
+            outputs = self.model["G"].forward(batch["in_feats"], enc_h, dec_h, spkrvec)
         real = self._discriminate(self.get_D_inputs(batch, batch["in_feats"], label="org"))
         loss = self.calculate_discriminator_loss(real, batch["org_h"], mask, loss, label="real")
         fake = self._discriminate(self.get_D_inputs(batch, outputs["decoded"].detach(), label="cv"))

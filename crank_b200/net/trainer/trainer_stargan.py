@@ -2,6 +2,8 @@
 
 import random
 
+import torch
+
 from .trainer_lsgan import LSGANTrainer
 
 
@@ -28,7 +30,8 @@ class StarGANTrainer(LSGANTrainer):
         real = self._discriminate(self.get_D_inputs(batch, batch["in_feats"], label="org"))
         loss = self.calculate_discriminator_loss(real, batch["org_h"], batch["decoder_mask"], loss,
                                                  label="real", updates=updates)
-        outputs = self.model["G"].forward(batch["in_feats"], enc_h_cv, dec_h_cv, spkrvec_cv)
+        with torch.no_grad():       # only decoded.detach() is used
+            outputs = self.model["G"].forward(batch["in_feats"], enc_h_cv, dec_h_cv, spkrvec_cv)
         fake = self._discriminate(self.get_D_inputs(batch, outputs["decoded"].detach(), label="cv"))
         loss = self.calculate_discriminator_loss(fake, batch["cv_h"], batch["decoder_mask"], loss,
                                                  label="fake", updates=updates)

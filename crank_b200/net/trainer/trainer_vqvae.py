@@ -121,8 +121,12 @@ class VQVAETrainer(BaseTrainer):
             enc_h = self._get_enc_h(batch)
             dec_h, spkrvec = self._get_dec_h(batch)
             # the reference re-runs G here (trainer_vqvae.py:168); kept: the EMA codebook update
-            # fires on every G forward, so dropping the pass would change the training trajectory
-            outputs = self.model["G"].forward(self._feats(batch), enc_h, dec_h, spkrvec=spkrvec)
+            # fires on every G forward, so dropping the pass would change the training trajectory.
+            # Only the (detached) encoder outputs are read: no autograd graph, and the bottom decoder
+            # stack -- stateless, feeding no quantiser -- is not evaluated
+            with torch.no_grad():
+                outputs = self.model["G"].forward(self._feats(batch), enc_h, dec_h, spkrvec=spkrvec,
+                                                  final_decoder=False)
             encoded, er = self._encoder_outputs(outputs)
             logits = self.model["SPKRADV"].forward(encoded, detach=True)
             ce = self.criterion["ce"](logits.reshape(-1, logits.size(2)), batch["org_h"][:, er:].reshape(-1))

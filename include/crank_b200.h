@@ -124,6 +124,13 @@ int crk_wavenet_fwd(const crk_wavenet_cfg* cfg, const float* weff, const float* 
                     const float* c, int ldc, const float* dropmul, float* y, int ldy, float* act,
                     int B, int T, void* stream);
 
+/* forward without the state backward needs (inference: reconstruction / eval / conversion, and the no-grad
+ * generator passes of the GAN train steps): same arguments and result as crk_wavenet_fwd, `act` is scratch of the
+ * same size, the per-layer (tanh, sigmoid) pairs are not written. */
+int crk_wavenet_infer(const crk_wavenet_cfg* cfg, const float* weff, const float* x, int ldx,
+                      const float* c, int ldc, const float* dropmul, float* y, int ldy, float* act,
+                      int B, int T, void* stream);
+
 /* backward.  dy (B*T,out_ch) ld lddy -> gtheta (same layout as theta, overwritten; NULL = parameters
  * frozen: only input gradients are computed and every weight-gradient kernel is skipped),
  * dx (B*T,in_ch) ld lddx or NULL, dc (B*T,aux_ch) ld lddc or NULL (overwritten).

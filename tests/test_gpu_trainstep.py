@@ -213,3 +213,36 @@ def test_frozen_forward_skips_weight_gradients_but_keeps_input_gradient():
     n1 = L.lib().crk_launch_count()
     D.forward_cl(xc).backward(dy)
     assert n_frozen < L.lib().crk_launch_count() - n1      # fewer kernels: no wgrad / reduce / weight-norm backward
+
+
+def test_no_grad_forward_and_skipped_final_decoder_are_invisible():
+    """The no-grad generator passes use crk_wavenet_infer (no saved gates) and the speaker-adversarial update skips
+    the bottom decoder: outputs, encoder outputs and the EMA codebook state must be bit-identical to the full pass."""
+    import copy
+
+    from crank_b200.conf import vcc2020_conf
+    from crank_b200.net.module.vqvae2 import VQVAE2
+
+    conf = vcc2020_conf(trainer_type="lsgan")
+    torch.manual_seed(11)
+    Ga = VQVAE2(conf, spkr_size=4).cuda()
+    Gb = copy.deepcopy(Ga)
+    Gc = copy.deepcopy(Ga)
+    B, T = 3, 160
+    x = torch.randn(B, T, 80, device="cuda")
+    dec_h = torch.randn(B, T, 2, device="cuda")
+    spk = torch.randint(0, 4, (B, 1), device="cuda").expand(B, T).contiguous()
+    oa = Ga.forward(x, None, dec_h, spkrvec=spk)
+    with torch.no_grad():
+        ob = Gb.forward(x, None, dec_h, spkrvec=spk)
+        oc = Gc.forward(x, None, dec_h, spkrvec=spk, final_decoder=False)
+    assert torch.equal(oa["decoded"], ob["decoded"])
+    assert oc["decoded"] is None
+    for n in range(conf["n_vq_stacks"]):
+        assert torch.equal(oa["encoded_unmod"][n], ob["encoded_unmod"][n])
+        assert torch.equal(oa["encoded_unmod"][n], oc["encoded_unmod"][n])
+        assert torch.equal(oa["qidx"][n], oc["qidx"][n])
+        for other in (Gb, Gc):
+            assert torch.equal(Ga.quantizers[n].ema_w, other.quantizers[n].ema_w)
+            assert torch.equal(Ga.quantizers[n].ema_size, other.quantizers[n].ema_size)
+            assert torch.equal(Ga.quantizers[n].embedding.weight, other.quantizers[n].embedding.weight)
