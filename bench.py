@@ -305,6 +305,33 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
 
+    # ---- data path: batch assembly on the device from a resident corpus ----------
+    data_path = None
+    if rank == 0:
+        from crank_b200.data import DeviceBatcher, UtteranceStore
+
+        rs = np.random.RandomState(0)
+        names = [f"spk{i}" for i in range(N_SPKRS)]
+        utts = [{"mlfb": rs.randn(n, 80).astype(np.float32), "lcf0": 5.0 + 0.2 * rs.randn(n), "uv": (rs.rand(n) < 0.7) * 1.0,
+                 "spkr": names[i % N_SPKRS]} for i, n in enumerate(rs.randint(300, 900, size=256))]
+        store = UtteranceStore(utts, names, None, device=dev)
+        batcher = DeviceBatcher(store, T)
+        idx = [int(i) for i in rs.randint(0, len(utts), size=B)]
+        for _ in range(3):
+            batcher.make_batch(idx)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(10):
+            batcher.make_batch(idx)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / 10
+        data_path = {"what": "crank_b200.data.DeviceBatcher.make_batch: gather / crop / pad / mask / one-hot / F0 conversion on "
+                             "the device from an HBM-resident corpus (replaces BaseDataset.__getitem__ + collate + H2D)",
+                     "ms_per_batch_device": e0.elapsed_time(e1) / 10, "ms_per_batch_wall": wall * 1e3,
+                     "frames_per_s_wall": B * T / wall, "corpus_frames": store.n_frames}
     if rank == 0:
         peaks, peaks_src = measured_peaks()
         F = B * T
@@ -356,6 +383,7 @@ def run_b200(args, rank, local_rank, world):
                           "frac": (vq_gbs / peaks["hbm_gbs"]) if vq_gbs and peaks.get("hbm_gbs") else None,
                           "bytes_per_frame": 520},
             "kernels": kern,
+            "data_path": data_path,
         }
         if not args.no_cpu_baseline and world == 1:
             fps, sec, threads = cpu_reference_throughput(kind, args.cpu_batch, T, 3, 1)
