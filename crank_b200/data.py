@@ -164,3 +164,38 @@ class DeviceBatcher:
             if len(idx) < batch_size and drop_last:
                 break
             yield self.make_batch(idx)
+
+
+class DeviceLoader:
+    """Iterable with the DataLoader role (len / iteration over one epoch; no drop_last, like the reference's loaders)."""
+
+    def __init__(self, batcher, batch_size, shuffle):
+        self.batcher, self.batch_size, self.shuffle = batcher, max(int(batch_size), 1), shuffle
+
+    def __len__(self):
+        n = len(self.batcher.store)
+        return (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        return self.batcher.epoch(self.batch_size, shuffle=self.shuffle, drop_last=False)
+
+
+def get_device_dataloader(conf, corpora, spkrs, scaler, flag="train", device="cuda"):
+    """Device-resident counterpart of `get_dataloader` (crank/net/trainer/utils.py:77-109): the same
+    {"spkrs", "train", "dev", "eval"} dict the trainers take.  corpora: {"train"/"dev"/"eval": [utterance dicts]}.
+    For `reconstruction` / `eval` the reference converts its (batch_len x batch_size) token budget into
+    whole-utterance batches: batch_len = longest utterance, batch_size = tokens // batch_len (utils.py:85-88)."""
+    batch_len, batch_size = int(conf["batch_len"]), int(conf["batch_size"])
+    if flag in ("reconstruction", "eval"):
+        pool = corpora.get("eval", []) if flag == "eval" else corpora.get("train", []) + corpora.get("dev", [])
+        ft = conf["input_feat_type"]
+        token_size = batch_len * batch_size
+        batch_len = max(int(np.asarray(u[ft]).shape[0]) for u in pool)
+        batch_size = max(token_size // batch_len, 1)
+    out = {"spkrs": {s: i for i, s in enumerate(spkrs)}}
+    for phase, shuffle in (("train", True), ("dev", True), ("eval", False)):
+        if corpora.get(phase):
+            store = UtteranceStore(corpora[phase], spkrs, scaler, feat_type=conf["input_feat_type"], device=device,
+                                   ignore_scaler=conf.get("ignore_scaler", ()))
+            out[phase] = DeviceLoader(DeviceBatcher(store, batch_len), batch_size, shuffle)
+    return out

@@ -100,3 +100,26 @@ def test_epoch_iterator_covers_the_corpus_once():
         assert batch["in_feats"].shape == (4, BATCH_LEN, 80)
         seen += batch["flbl"]
     assert sorted(seen) == sorted(u["flbl"] for u in utts)
+
+
+def test_device_dataloader_token_budget_for_eval():
+    """utils.py:85-88: eval / reconstruction batches hold whole utterances under the training token budget."""
+    from crank_b200.data import get_device_dataloader
+    from oracle import dataset_port as dp
+
+    utts, scaler = dp.make_corpus(12, SPKRS, seed=1)
+    conf = {"batch_len": 100, "batch_size": 8, "input_feat_type": "mlfb", "ignore_scaler": []}
+    corpora = {"train": utts[:8], "dev": utts[8:10], "eval": utts[4:]}
+    dl = get_device_dataloader(conf, corpora, SPKRS, scaler, flag="train", device="cpu")
+    assert set(dl) == {"spkrs", "train", "dev", "eval"} and dl["spkrs"]["TM2"] == 4
+    b = next(iter(dl["train"]))
+    assert b["in_feats"].shape == (8, 100, 80)
+    de = get_device_dataloader(conf, corpora, SPKRS, scaler, flag="eval", device="cpu")
+    longest = max(u["mlfb"].shape[0] for u in corpora["eval"])
+    batches = list(de["eval"])
+    assert all(x["in_feats"].shape[1] == longest for x in batches)
+    assert batches[0]["in_feats"].shape[0] == max(800 // longest, 1)
+    assert sum(x["in_feats"].shape[0] for x in batches) == len(corpora["eval"])
+    # whole utterances: nothing cropped, every valid frame kept
+    for x in batches:
+        assert torch.equal(x["encoder_mask"].sum(dim=(1, 2)), torch.minimum(x["flen"], torch.tensor(longest)))
