@@ -160,7 +160,8 @@ class ClockSampler:
 def ncu_traffic(family):
     """DRAM bytes (read + write) of one launch of the family's kernel from the committed `ncu --set full`
     capture (profiles/ncu_traffic_r1b.json; produced by profiles/call_ncu.sh on the same workload)."""
-    name = {"resblock_fwd": "k_resblock_fwd_tc", "conv": "k_conv_tc", "wgrad": "k_wgrad_tc_raw"}.get(family)
+    name = {"resblock_fwd": "k_resblock_fwd_tc", "conv": "k_conv_tc", "wgrad": "k_wgrad_tc_raw",
+            "vq_argmin": "k_vq_argmin_tc"}.get(family)
     p = os.path.join(ROOT, "profiles", "ncu_traffic_r1b.json")
     if name is None or not os.path.exists(p):
         return None, None
@@ -381,7 +382,8 @@ def run_b200(args, rank, local_rank, world):
             },
             "vq_argmin": {"algorithmic_GBps": vq_gbs, "hbm_peak_GBps": peaks.get("hbm_gbs"),
                           "frac": (vq_gbs / peaks["hbm_gbs"]) if vq_gbs and peaks.get("hbm_gbs") else None,
-                          "bytes_per_frame": 520},
+                          "bytes_per_frame": 520,
+                          "traffic": ncu_traffic("vq_argmin")[0] if args.precision != "fp32" else None},
             "kernels": kern,
             "data_path": data_path,
         }

@@ -64,7 +64,7 @@ def full(kernel):
 
 with open(os.path.join(ROOT, "profiles", f"launches_{ROUND}_{PREC}.md"), "w") as f:
     f.write(launches() + "\n")
-KERNELS = ["k_resblock_fwd_tc", "k_conv_tc", "k_wgrad_tc_raw", "k_wgrad_tc", "k_vq_argmin"]
+KERNELS = ["k_resblock_fwd_tc", "k_conv_tc", "k_wgrad_tc_raw", "k_wgrad_tc", "k_vq_argmin_tc"]
 if any(os.path.exists(os.path.join(OUT, f"prof_{k}_{PREC}.ncu-rep")) for k in KERNELS):   # keep the last summary otherwise
     with open(os.path.join(ROOT, "profiles", f"ncu_full_{ROUND}_{PREC}.md"), "w") as f:
         f.write(f"# ncu --set full summaries ({ROUND}, {PREC}); .ncu-rep files stay in gpurun_out/ (scratch)\n\n")
