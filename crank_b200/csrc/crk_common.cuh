@@ -79,7 +79,10 @@ inline int& opt_disable_mask() { static int m = 0; return m; }
 // following its drain.  Contract kept by every kernel launched through launch_pdl(): NO global memory
 // access before pdl_wait() (which returns once the predecessor grid has completed and its writes are
 // visible), so the result is identical to plain stream order.  Both instructions are no-ops in a
-// kernel launched without the attribute.
+// kernel launched without the attribute.  Kernels that allocate tensor memory trigger AFTER the
+// allocation: a dependent CTA that became co-resident on the same SM (possible in the plain-TF32 variants,
+// two CTAs per SM) and grabbed the TMEM columns first would then wait for a predecessor that can never
+// get its own -- a deadlock by construction, however unlikely the interleaving.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

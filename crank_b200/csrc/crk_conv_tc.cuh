@@ -214,7 +214,6 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
-    pdl_trigger();
     const int tiles_per_utt = (p.T + CRK_TC_TM - 1) / CRK_TC_TM;
     const int b = blockIdx.x / tiles_per_utt;
     const int t0 = (blockIdx.x - b * tiles_per_utt) * CRK_TC_TM;
@@ -255,6 +254,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     bool ok = true;
+    pdl_trigger();                                      // only now: this CTA already owns its TMEM columns (see crk_common.cuh)
     pdl_wait();
     dbg_stamp(q.dbg, 0);
     if (threadIdx.x == 0)

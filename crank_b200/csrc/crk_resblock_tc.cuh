@@ -198,7 +198,6 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
-    pdl_trigger();                                      // the next kernel may start its prologue
     const int tiles_per_utt = (p.T + CRK_TC_TM - 1) / CRK_TC_TM;
     const int b = blockIdx.x / tiles_per_utt;
     const int t0 = (blockIdx.x - b * tiles_per_utt) * CRK_TC_TM;
@@ -241,6 +240,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_resblock_fwd_tc(const Re
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     bool ok = true;
+    pdl_trigger();                                      // only now: this CTA already owns its TMEM columns (see crk_common.cuh)
     pdl_wait();                                         // predecessor complete: global memory may be touched
     dbg_stamp(q.dbg, 0);
 

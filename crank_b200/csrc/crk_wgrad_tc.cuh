@@ -116,7 +116,6 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
-    pdl_trigger();
     constexpr int KCH = CRK_WG_TF / 4;                     // 16 frame chunks per tile
     constexpr int CSG = 129 * 4;                           // G^T: 128 rows -> 129
     const int csx = tc::chunk_rows(q.Npad) * 4;
@@ -163,6 +162,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     float4 bsum[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) bsum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_trigger();                                      // only now: this CTA already owns its TMEM columns (see crk_common.cuh)
     pdl_wait();
     auto load_x = [&](int tile, int j) {
         const int bb = tile / tiles_per_utt;
@@ -389,7 +389,6 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
-    pdl_trigger();
     constexpr int KCH = CRK_WG_TF / 4;
     constexpr int CSG = 129 * 4;
     const int csx = tc::chunk_rows(q.Npad) * 4;
@@ -429,6 +428,7 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     float4 bsum[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) bsum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_trigger();                                      // only now: this CTA already owns its TMEM columns (see crk_common.cuh)
     pdl_wait();
 
     if (worker) {
