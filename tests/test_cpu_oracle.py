@@ -223,3 +223,50 @@ def test_synthetic_batch_schema():
         assert (b["org_h"][i, n:] == -100).all() and (b["org_h"][i, :n] >= 0).all()
         assert not b["decoder_mask"][i, n:].any() and b["in_feats"][i, n:].abs().sum() == 0
     assert ((b["cv_h"][:, 0] - b["org_h"][:, 0]) % 14 == 1).all()
+
+
+def test_conf_defaults_equal_the_reference_default_yaml():
+    """crank_b200.conf mirrors egs/vaevc/template/conf/default.yml key by key (every tensor shape on the hot path
+    derives from it); checked against the reference checkout when it is present."""
+    import yaml
+
+    from crank_b200.conf import default_conf
+    from oracle import refshim
+
+    path = os.path.join(refshim.REFERENCE_ROOT, "egs", "vaevc", "template", "conf", "default.yml")
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present on this box")
+
+    def flat(d, pre=""):
+        out = {}
+        for k, v in d.items():
+            if isinstance(v, dict):
+                out.update(flat(v, pre + k + "."))
+            else:
+                out[pre + k] = v
+        return out
+
+    ref, mine = flat(yaml.safe_load(open(path))), flat(default_conf())
+    assert set(ref) == set(mine), (sorted(set(ref) - set(mine)), sorted(set(mine) - set(ref)))
+    diff = {k: (ref[k], mine[k]) for k in ref if ref[k] != mine[k]}
+    assert not diff, diff
+
+
+def test_frozen_context_restores_requires_grad_even_on_error():
+    from crank_b200.net.trainer.basetrainer import frozen
+
+    m = torch.nn.Linear(3, 2)
+    m.bias.requires_grad_(False)                       # already frozen parameters stay frozen afterwards
+    with frozen(m):
+        assert not m.weight.requires_grad
+        y = m(torch.ones(1, 3, requires_grad=True))
+    assert m.weight.requires_grad and not m.bias.requires_grad
+    x = torch.ones(1, 3, requires_grad=True)
+    with frozen(m):
+        out = m(x).sum()
+    out.backward()
+    assert m.weight.grad is None and x.grad is not None
+    with pytest.raises(RuntimeError):
+        with frozen(m):
+            raise RuntimeError("boom")
+    assert m.weight.requires_grad
