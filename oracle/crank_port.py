@@ -495,6 +495,11 @@ class OracleTrainer:
                 for io in ["org", "cv"]:
                     lbl = f"{cyc}cyc_{io}"
                     D_out = self._D(self._D_inputs(b, outs[cyc][io]["decoded"], label="cv"))
+                    if c["acgan_flag"]:      # trainer_cyclegan.py:107-118: only this branch masks the adversarial term
+                        D_out, cls = torch.split(D_out, [1, len_spk(D_out) - 1], dim=2)
+                        D_out = D_out.masked_select(b["decoder_mask"])
+                        loss[f"D_acgan_adv_{lbl}"] = self.ce(cls.reshape(-1, cls.size(2)), b[f"{io}_h"].reshape(-1))
+                        loss["G"] += c["alpha"]["acgan"] * loss[f"D_acgan_adv_{lbl}"]
                     loss[f"D_adv_{lbl}"] = F.mse_loss(D_out, torch.ones_like(D_out))
                     loss["G"] += c["alpha"]["adv"] * loss[f"D_adv_{lbl}"]
         else:  # stargan
@@ -532,6 +537,13 @@ class OracleTrainer:
                     "org_fake": self._D(self._D_inputs(b, outs[0]["org"]["decoded"].detach(), "org")),
                     "cv_fake": self._D(self._D_inputs(b, outs[0]["cv"]["decoded"].detach(), "cv")),
                 }
+                if c["acgan_flag"]:          # trainer_cyclegan.py:143-159
+                    for k in list(sample.keys()):
+                        h = b["org_h"] if k in ["real", "org_fake"] else b["cv_h"]
+                        sample[k], cls = torch.split(sample[k], [1, len_spk(sample[k]) - 1], dim=2)
+                        loss[f"D_ce_{k}_{lbl}"] = self.ce(cls.reshape(-1, cls.size(2)), h.reshape(-1))
+                        if not (c["use_real_only_acgan"] and k == "org_fake"):
+                            loss["D"] += c["alpha"]["acgan"] * loss[f"D_ce_{k}_{lbl}"]
                 rs = sample["real"].masked_select(b["decoder_mask"])
                 loss[f"D_real_{lbl}"] = F.mse_loss(rs, torch.ones_like(rs))
                 fake_key = random.choice(["org_fake", "cv_fake"])

@@ -86,8 +86,7 @@ def test_oracle_port_reproduces_reference_golden(kind):
     np.testing.assert_allclose(fin, gold[f"{kind}/final_checksum"], rtol=1e-9)
 
 
-@pytest.mark.parametrize("kind", ["vqvae", "lsgan"])
-def test_oracle_port_is_bit_identical_to_live_reference(kind):
+def _oracle_vs_live_reference(kind, overrides, T=80):
     from oracle import refshim
 
     if not refshim.available():
@@ -102,7 +101,7 @@ def test_oracle_port_is_bit_identical_to_live_reference(kind):
     tr = refshim.ref("crank.net.trainer")
     tu = refshim.ref("crank.net.trainer.utils")
     S = 5
-    conf = vcc2020_conf(trainer_type=kind, n_steps_gan_start=-1, discriminator_dropout=0.0)
+    conf = vcc2020_conf(trainer_type=kind, n_steps_gan_start=-1, discriminator_dropout=0.0, **overrides)
     torch.manual_seed(7)
     ref_m = {"G": vq.VQVAE2(conf, spkr_size=S), "SPKRADV": spk.SpeakerAdversarialNetwork(conf, S)}
     extra = cp.build_models(conf, S)
@@ -114,14 +113,16 @@ def test_oracle_port_is_bit_identical_to_live_reference(kind):
         om[k].load_state_dict(ref_m[k].state_dict())
     opt = tu.get_optimizer(conf, ref_m)
     W = refshim.NullWriter()
-    T = tr.TrainerWrapper(kind, model=ref_m, optimizer=opt, criterion=tu.get_criterion(conf, device="cpu"),
-                          dataloader={"spkrs": spkr_dict(S)}, writer={"train": W, "dev": W}, expdir="/tmp/exp",
-                          conf=conf, feat_conf=conf["feature"], scheduler=tu.get_scheduler(conf, opt), scaler=None,
-                          resume=0, device="cpu", n_jobs=1)
-    T.tqdm.close()
+    T_ = tr.TrainerWrapper(kind, model=ref_m, optimizer=opt, criterion=tu.get_criterion(conf, device="cpu"),
+                           dataloader={"spkrs": spkr_dict(S)}, writer={"train": W, "dev": W}, expdir="/tmp/exp",
+                           conf=conf, feat_conf=conf["feature"], scheduler=tu.get_scheduler(conf, opt), scaler=None,
+                           resume=0, device="cpu", n_jobs=1)
+    T_.tqdm.close()
     O = cp.OracleTrainer(kind, om, cp.build_optimizers(conf, om), conf)
-    b = make_batch(2, 80, S, seed=3, ragged=True)
-    r = T.train(clone_batch(b), "train")
+    b = make_batch(2, T, S, seed=3, ragged=True)
+    random.seed(1)                      # cyclegan / stargan draw host-side choices (trainer_cyclegan.py:166)
+    r = T_.train(clone_batch(b), "train")
+    random.seed(1)
     o = O.train(clone_batch(b), "train")
     assert set(r) == set(o)
     for k in r:
@@ -129,6 +130,29 @@ def test_oracle_port_is_bit_identical_to_live_reference(kind):
     for k in om:
         for (n1, p1), (n2, p2) in zip(ref_m[k].state_dict().items(), om[k].state_dict().items()):
             assert n1 == n2 and torch.equal(p1, p2), (k, n1)
+
+
+@pytest.mark.parametrize("kind", ["vqvae", "lsgan", "cyclegan", "stargan"])
+def test_oracle_port_is_bit_identical_to_live_reference(kind):
+    _oracle_vs_live_reference(kind, {})
+
+
+@pytest.mark.parametrize("kind,overrides", [
+    ("lsgan", dict(causal=True, causal_size=4)),       # left padding, shifted losses, receptive-field crop (Appendix A)
+    ("cyclegan", dict(n_vq_stacks=3)),
+    ("vqvae", dict(n_vq_stacks=1)),
+    ("lsgan", dict(use_spkr_embedding=False)),         # one-hot speaker code instead of the embedding
+    ("cyclegan", dict(encoder_f0=True)),
+    ("lsgan", dict(ema_flag=False)),                   # dictionary loss + codebook gradient instead of EMA
+    ("cyclegan", dict(acgan_flag=True)),
+    ("lsgan", dict(acgan_flag=True)),
+    ("stargan", dict(cvadv_flag=True)),
+    ("lsgan", dict(encoder_detach=True)),
+])
+def test_oracle_port_matches_live_reference_on_config_variants(kind, overrides):
+    """Every recipe switch that changes the train step's graph: loss dicts and all parameters after one step are
+    bit-identical to the unmodified reference trainers (causal needs frames beyond the receptive field)."""
+    _oracle_vs_live_reference(kind, overrides, T=160 if overrides.get("causal") else 80)
 
 
 def test_c_abi_library_exports_every_declared_symbol():
