@@ -106,9 +106,9 @@ def test_emulation_is_test_only_and_restored():
     from crank_b200 import lib, ops
     from crank_b200.parallel_wavegan import models
 
-    before = (models.WavenetFn, ops.VQFn, ops.masked_l1_mse, lib.require_cuda)
+    before = (models.WavenetFn, ops.VQFn, ops.MaskedLossFn, lib.require_cuda)
     with emulated_ops():
         assert models.WavenetFn is not before[0]
-    assert (models.WavenetFn, ops.VQFn, ops.masked_l1_mse, lib.require_cuda) == before
+    assert (models.WavenetFn, ops.VQFn, ops.MaskedLossFn, lib.require_cuda) == before
     with pytest.raises(lib.CrkError):
         ops.masked_l1_mse(torch.zeros(1, 2, 3), 0.0)          # the product still refuses CPU tensors
