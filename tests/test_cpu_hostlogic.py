@@ -112,3 +112,67 @@ def test_emulation_is_test_only_and_restored():
     assert (models.WavenetFn, ops.VQFn, ops.MaskedLossFn, lib.require_cuda) == before
     with pytest.raises(lib.CrkError):
         ops.masked_l1_mse(torch.zeros(1, 2, 3), 0.0)          # the product still refuses CPU tensors
+
+
+def test_conversion_conditioning_matches_live_reference():
+    """eval / dev / reconstruction: the conditioning tensors built for a TARGET speaker (`_get_enc_h`, `_get_dec_h`,
+    log-F0 conversion through the scalers, basetrainer.py:253-320) equal the reference trainer's, and the no-grad
+    conversion pass (`_convert`) equals the oracle generator on those conditions."""
+    from oracle import refshim
+
+    if not refshim.available():
+        pytest.skip("/root/reference is not present on this box")
+    from sklearn.preprocessing import StandardScaler
+
+    from crank_b200.conf import vcc2020_conf
+    from crank_b200.net.trainer import TrainerWrapper, get_criterion, get_model, get_optimizer, get_scheduler
+    from crank_b200.synthetic import clone_batch, make_batch, spkr_dict
+    from oracle import crank_port as cp
+
+    refshim.install()
+    tr = refshim.ref("crank.net.trainer")
+    tu = refshim.ref("crank.net.trainer.utils")
+    conf = vcc2020_conf(trainer_type="vqvae", encoder_f0=True)
+    rs = np.random.RandomState(0)
+    names = list(spkr_dict(S).keys())
+    scaler = {"lcf0": StandardScaler().fit(5.0 + 0.3 * rs.randn(500, 1))}
+    for i, n in enumerate(names):
+        scaler[n] = {"lcf0": StandardScaler().fit(4.6 + 0.2 * i + (0.15 + 0.02 * i) * rs.randn(300, 1))}
+    torch.manual_seed(2)
+    om = cp.build_models(conf, S)
+    ropt = tu.get_optimizer(conf, om)
+    R = tr.TrainerWrapper("vqvae", model=om, optimizer=ropt, criterion=tu.get_criterion(conf, device="cpu"),
+                          dataloader={"spkrs": spkr_dict(S)}, writer={"train": _W(), "dev": _W()}, expdir="/tmp/exp",
+                          conf=conf, feat_conf=conf["feature"], scheduler=tu.get_scheduler(conf, ropt), scaler=scaler,
+                          resume=0, device="cpu", n_jobs=1)
+    R.tqdm.close()
+    b = make_batch(3, 64, S, seed=9, ragged=True)
+    target = names[3]
+    with emulated_ops():
+        pm = get_model(conf, S, device="cpu")
+        for k in om:
+            pm[k].load_state_dict(om[k].state_dict())
+        popt = get_optimizer(conf, pm)
+        P = TrainerWrapper("vqvae", model=pm, optimizer=popt, criterion=get_criterion(conf),
+                           dataloader={"spkrs": spkr_dict(S)}, writer={"train": _W(), "dev": _W()}, expdir="/tmp/exp",
+                           conf=conf, feat_conf=conf["feature"], scheduler=get_scheduler(conf, popt), scaler=scaler,
+                           resume=0, device="cpu", n_jobs=1)
+        P.tqdm.close()
+        for kw in (dict(cv_spkr_name=target), dict(use_cvfeats=True), dict()):
+            re_h, pe_h = R._get_enc_h(clone_batch(b), **kw), P._get_enc_h(clone_batch(b), **kw)
+            assert torch.allclose(re_h, pe_h, atol=2e-5), kw
+            (rd, rh), (pd, ph) = R._get_dec_h(clone_batch(b), **kw), P._get_dec_h(clone_batch(b), **kw)
+            assert torch.allclose(rd, pd, atol=2e-5) and torch.equal(rh, ph), kw
+        for p_ in pm.values():
+            p_.eval()
+        for o_ in om.values():
+            o_.eval()
+        out = P.eval(clone_batch(b))[target]            # @torch.no_grad entry point: one conversion per target speaker
+        enc_h = R._get_enc_h(clone_batch(b), cv_spkr_name=target)
+        dec_h, spkrvec = R._get_dec_h(clone_batch(b), cv_spkr_name=target)
+        with torch.no_grad():
+            ref = om["G"].forward(b["in_feats"], enc_h, dec_h, spkrvec=spkrvec)
+        assert not out["decoded"].requires_grad
+        assert torch.allclose(out["decoded"], ref["decoded"], atol=1e-4, rtol=1e-4)
+        for n in range(conf["n_vq_stacks"]):
+            assert torch.equal(out["qidx"][n], ref["qidx"][n])
