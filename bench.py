@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--trainer", default="lsgan", choices=["vqvae", "lsgan", "cyclegan", "stargan"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="utterances of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager-gpu-baseline", action="store_true",
+                    help="also time the reference's own graph (the oracle port, stock PyTorch eager: cuDNN / cuBLAS) on "
+                         "this GPU at the bench batch -- SURVEY.md section 8d's 'reference GPU path' bar; reported as "
+                         "`torch_eager_gpu_baseline`, never part of value / e2e")
     ap.add_argument("--precision", default=os.environ.get("CRANK_B200_PRECISION", "tf32x3"),
                     choices=["fp32", "tf32x3", "tf32"],
                     help="conv contraction arithmetic: fp32 CUDA cores, 3xTF32 tcgen05 (parity mode), TF32 tcgen05")
@@ -94,6 +98,39 @@ def cpu_reference_throughput(kind, batch_utts, frames, steps, warmup):
         tr.train(clone_batch(batch), "train")
     dt = time.perf_counter() - t0
     return batch_utts * frames * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def eager_gpu_reference_throughput(kind, batch_utts, frames, steps, warmup, device):
+    """frames/s of the oracle port of the reference's trainer run by stock PyTorch eager ON THE GPU (device-timed).
+    A reported bar only: what the unmodified reference graph achieves on the same B200."""
+    import random
+
+    import numpy as np
+    import torch
+
+    from crank_b200.synthetic import clone_batch, make_batch, to_device
+    from oracle import crank_port as cp
+
+    conf = bench_conf(kind)
+    random.seed(1234)
+    np.random.seed(1234)
+    torch.manual_seed(1234)
+    models = cp.build_models(conf, N_SPKRS)
+    for m in models.values():
+        m.to(device)
+    tr = cp.OracleTrainer(kind, models, cp.build_optimizers(conf, models), conf)
+    batch = to_device(make_batch(batch_utts, frames, N_SPKRS, seed=0), device)
+    for _ in range(warmup):
+        tr.train(clone_batch(batch), "train")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.train(clone_batch(batch), "train")
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    return batch_utts * frames / sec, sec
 
 
 def cpu_model_name():
@@ -392,6 +429,15 @@ def run_b200(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                     "cpu": cpu_model_name(),
                                     "sample": f"{args.cpu_batch} utts x {T} frames per step, 1 warm-up + 3 timed steps"}
+        if args.eager_gpu_baseline and world == 1:
+            try:
+                fps, sec = eager_gpu_reference_throughput(kind, B, T, 5, 3, dev)
+                line["torch_eager_gpu_baseline"] = {
+                    "value": fps, "unit": "frames/s", "ms_per_step": sec * 1e3, "kind": "port",
+                    "what": "oracle/crank_port.py (bit-identical to the reference trainers on CPU) executed by stock "
+                            "PyTorch eager on this GPU, fp32, same batch; 3 warm-up + 5 timed steps"}
+            except Exception as err:     # the bar is optional: never lose the bench line over it
+                line["torch_eager_gpu_baseline"] = {"unavailable": repr(err)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
