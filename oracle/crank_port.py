@@ -251,7 +251,7 @@ def feature_loss(kind, x, y, mask=None, causal=False, causal_size=0):
 def stft_mag(x, n_fft, hop_length, win_length):
     """loss.py:50-60 with torch.stft's real parameter meaning spelled out."""
     x = x.transpose(1, 2).reshape(-1, x.size(1))
-    window = torch.hann_window(win_length)
+    window = torch.hann_window(win_length, device=x.device)      # (device-agnostic: bench.py --eager-gpu-baseline runs this port on the GPU)
     z = torch.stft(x, n_fft, hop_length, win_length, window, return_complex=True)
     y = torch.clamp(z.real ** 2 + z.imag ** 2, min=1e-7).transpose(2, 1)
     return torch.sqrt(y)
