@@ -294,3 +294,15 @@ def test_frozen_context_restores_requires_grad_even_on_error():
         with frozen(m):
             raise RuntimeError("boom")
     assert m.weight.requires_grad
+
+
+def test_missing_extension_fails_loudly(monkeypatch):
+    """No silent fallback: without the built library every op entry raises (and says how to build it)."""
+    from crank_b200 import lib
+
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libcrank_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
+        lib.lib()
+    with pytest.raises(RuntimeError):
+        lib.call("crk_adam_step")
