@@ -109,7 +109,7 @@ int crk_tc_probe(const float* A, int lda, int rowsA, const float* B, int ldb, in
 }
 
 int crk_tc_mma_rate(int N, int K, int reps, int split, int grid, long long* cycles, void* stream) {
-    if (!cycles || N < 16 || N > 128 || (N % 16) != 0 || K < 8 || K > 128 || (K % 8) != 0 || reps == 0 || grid < 1) return CRK_ERR_ARG;
+    if (!cycles || N < 16 || N > 256 || (N % 16) != 0 || K < 8 || K > 128 || (K % 8) != 0 || reps == 0 || grid < 1) return CRK_ERR_ARG;
     const size_t smem = (size_t)2 * (K / 4) * (137 * 4 + tc::chunk_rows(N) * 4) * sizeof(float);
     if (smem > 220 * 1024) return CRK_ERR_UNSUPPORTED;
     API_TRY(cudaFuncSetAttribute(k_tc_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));

@@ -137,13 +137,13 @@ __global__ void __launch_bounds__(128) k_tc_mma_rate(int N, int K, int reps, int
     for (int i = threadIdx.x; i < total; i += blockDim.x)
         smem[i] = rnd ? (float)((i * 2654435761u) >> 8) * (1.0f / 8388608.0f) - 1.0f : 0.f;
     if (threadIdx.x == 0) { tc::mbar_init(&mbar, 1); tc::fence_mbar_init(); }
-    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc<256>(&tmem_base);
+    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc<512>(&tmem_base);      // D: columns 0..255 (N <= 256), A (TS form): 256..383
     tc::fence_proxy_async_smem();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base;
-    const int a_tmem = (split >> 1) & 1;           // bit 1 of `split`: A operand from tensor memory (columns 128..)
+    const int a_tmem = (split >> 1) & 1;           // bit 1 of `split`: A operand from tensor memory (columns 256..)
     const int commit_each = (split >> 2) & 1;      // bit 2: tcgen05.commit to a scratch mbarrier after every group
     const int warp_issue = (split >> 3) & 1;       // bit 3: warp-collective issue (uniform datapath), elected lane
     split &= 1;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(128) k_tc_mma_rate(int N, int K, int reps, int
         float z[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) z[i] = 0.f;
-        for (int c = 0; c < 128; c += 32) tc::tmem_st32(tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + 128 + c, z);
+        for (int c = 0; c < 128; c += 32) tc::tmem_st32(tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + 256 + c, z);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncthreads();
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(128) k_tc_mma_rate(int N, int K, int reps, int
         c0 = clock64();
         for (int r = 0; r < reps; ++r) {
             if (a_tmem) {
-                if (split) tc_issue_ts<true>(tmem, tmem + 128, tmem + 128 + 64, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K > 64 ? 64 : K, idesc, acc);
-                else tc_issue_ts<false>(tmem, tmem + 128, tmem + 128 + 64, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K > 64 ? 64 : K, idesc, acc);
+                if (split) tc_issue_ts<true>(tmem, tmem + 256, tmem + 256 + 64, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K > 64 ? 64 : K, idesc, acc);
+                else tc_issue_ts<false>(tmem, tmem + 256, tmem + 256 + 64, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K > 64 ? 64 : K, idesc, acc);
             } else if (split) tc_issue_kmajor<true>(tmem, tc::smem_u32(a_hi), tc::smem_u32(a_lo), csA * 4, r & 7, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K, idesc, acc);
             else tc_issue_kmajor<false>(tmem, tc::smem_u32(a_hi), tc::smem_u32(a_lo), csA * 4, r & 7, tc::smem_u32(b_hi), tc::smem_u32(b_lo), csB * 4, K, idesc, acc);
             if (commit_each) tc::umma_commit(&scratch_bar);
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) k_tc_mma_rate(int N, int K, int reps, int
     if (threadIdx.x == 0) cycles[2 * blockIdx.x] = ok ? clock64() - c0 : -1;
     tc::tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc<256>(tmem);
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc<512>(tmem);
 }
 
 }  // namespace crk

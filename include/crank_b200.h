@@ -69,7 +69,8 @@ double crk_timing_flops(void);
 int crk_tc_probe(const float* A, int lda, int rowsA, const float* B, int ldb, int rowsB, float* D, int N,
                  int K, int row_shift, int mode, int split, void* stream);
 /* tcgen05 MMA-rate microbenchmark (performance characterisation, profiles/mma_rate.py): `grid` CTAs each issue
- * reps x (split ? 3 : 1) x K/8 MMAs of shape 128 x N x 8 (TF32) on zero tiles in the conv kernels' operand
+ * reps x (split & 1 ? 3 : 1) x K/8 MMAs of shape 128 x N x 8 (TF32, N <= 256; split bit 1: A operand from
+ * tensor memory, bit 2: commit after every group, bit 3: warp-collective issue; reps < 0: random data) on tiles in the conv kernels' operand
  * layout; cycles[2*cta] = clock64 span issue..completion, cycles[2*cta+1] = span of the issue loop alone. */
 int crk_tc_mma_rate(int N, int K, int reps, int split, int grid, long long* cycles, void* stream);
 

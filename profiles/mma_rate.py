@@ -8,7 +8,7 @@ buf = torch.zeros(2 * 148, dtype=torch.int64, device="cuda")
 print("N   K   split grid | MMAs  cycles/MMA (exec)  cycles/MMA (issue loop)   [data: zeros, then random]")
 for grid in (148,):
     for split in (1, 9, 0, 8):        # bit 0: 3xTF32 passes, bit 1: A from tensor memory, bit 2: commit per group, bit 3: warp-collective issue
-        for N, K in ((128, 64), (64, 64), (64, 32), (64, 16), (16, 64)):
+        for N, K in ((256, 64), (192, 64), (128, 64), (64, 64), (64, 32), (16, 64)):
             reps = 40
             nmma = reps * (3 if split & 1 else 1) * (min(K, 64) if split & 2 else K) // 8
             out = []
