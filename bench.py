@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--trainer", default="lsgan", choices=["vqvae", "lsgan", "cyclegan", "stargan"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="utterances of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="EXPERIMENTAL (not yet validated on hardware): replay the step from a whole-step CUDA graph "
+                         "(crank_b200/net/graph.py); lsgan / vqvae trainers only")
     ap.add_argument("--eager-gpu-baseline", action="store_true",
                     help="also time the reference's own graph (the oracle port, stock PyTorch eager: cuDNN / cuBLAS) on "
                          "this GPU at the bench batch -- SURVEY.md section 8d's 'reference GPU path' bar; reported as "
@@ -281,12 +284,19 @@ def run_b200(args, rank, local_rank, world):
     h2d = sum(v.numel() * v.element_size() for v in host_batch.values() if isinstance(v, torch.Tensor))
     dev_batch = to_device(host_batch, dev)
 
+    run_step = trainer.train
+    if args.graph:
+        from crank_b200.net.graph import GraphedTrainStep
+
+        stepper = GraphedTrainStep(trainer)
+        run_step = lambda b, phase: stepper(b)      # noqa: E731
+
     def step_resident():
         b = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in dev_batch.items()}
-        return trainer.train(b, "train")
+        return run_step(b, "train")
 
     def step_e2e():
-        return trainer.train(to_device(host_batch, dev, non_blocking=True), "train")
+        return run_step(to_device(host_batch, dev, non_blocking=True), "train")
 
     def sync_all():
         if world > 1:
@@ -396,7 +406,7 @@ def run_b200(args, rank, local_rank, world):
                 "workload": f"VCC2020 conf/mlfb_vqvae.yml trainer_type={kind} (GAN phase), {B} utts/GPU x {T} "
                             f"frames, 14 speakers, 80-dim mlfb, discriminator dropout 0.25",
                 "trainer": kind, "batch_per_gpu": B, "global_batch": B * world, "frames": T,
-                "parallelism": f"dp{world}",
+                "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
                 "precision": {"fp32": "fp32 CUDA-core kernels", "tf32x3": "3xTF32 (error-compensated) tcgen05 tensor cores, fp32 accumulate",
                               "tf32": "TF32 tcgen05 tensor cores, fp32 accumulate"}[args.precision],
                 "l2": "per-step working set (saved activations ~0.7 GB per G forward at 64x500) exceeds the 126 MB L2; no explicit flush",

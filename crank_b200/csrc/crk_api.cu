@@ -458,6 +458,16 @@ int crk_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
     return CRK_OK;
 }
 
+int crk_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                      float beta2, float eps, long long* step_dev, void* stream) {
+    if (!p || !g || !m || !v || !step_dev || n < 1) return CRK_ERR_ARG;
+    k_step_inc<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    API_TRY(launch_check());
+    k_adam_dev<<<(unsigned)cdivl(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+
 }  // extern "C"
 
 // ---- log-mel front end -------------------------------------------------------------------------

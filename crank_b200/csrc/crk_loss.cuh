@@ -412,4 +412,27 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     p[i] = p[i] - step_size * (mi / denom);
 }
 
+
+// Graph-capturable variant: the step count lives in device memory (a captured launch cannot carry a host value
+// that changes every replay).  k_step_inc runs first; every block of k_adam_dev then derives the same bias
+// corrections from the incremented counter, in double like the host path of crk_adam_step.
+__global__ void k_step_inc(long long* step) { step[0] += 1; }
+__global__ void k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                           float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                           const long long* __restrict__ step) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double st = (double)step[0];
+    const double bc1 = 1.0 - pow((double)beta1, st);
+    const double bc2 = 1.0 - pow((double)beta2, st);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float gi = g[i];
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+    const float vi = fmaf(gi * gi, 1.f - beta2, v[i] * beta2);
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+}
+
 }  // namespace crk

@@ -9,8 +9,12 @@ from ... import ops
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """capturable=True keeps the step count in device memory (crk_adam_step_dev) so that the optimizer step can be
+    captured in a CUDA graph; the default passes it as a host integer (crk_adam_step)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.capturable = bool(capturable)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -28,10 +32,16 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                ops.adam_step(p.data, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), b1, b2,
-                              group["eps"], st["step"])
+                if self.capturable:
+                    if "step_dev" not in st:        # (created outside any capture: the first steps run eagerly)
+                        st["step_dev"] = torch.full((1,), int(st["step"]), dtype=torch.int64, device=p.device)
+                    ops.adam_step_dev(p.data, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), b1, b2,
+                                      group["eps"], st["step_dev"])
+                else:
+                    st["step"] += 1
+                    ops.adam_step(p.data, g, st["exp_avg"], st["exp_avg_sq"], float(group["lr"]), b1, b2,
+                                  group["eps"], st["step"])
                 # the kernel wrote through the raw pointer: bump the autograd version so that the
                 # weight-norm caches keyed on it (parallel_wavegan.models) are invalidated
                 torch.autograd.graph.increment_version(p)

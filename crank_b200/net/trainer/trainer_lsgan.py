@@ -32,7 +32,7 @@ class LSGANTrainer(VQVAETrainer):
         self._check_cycle_start()
         self._check_gan_start()
 
-    def train(self, batch, phase="train"):
+    def _train_core(self, batch, phase="train"):
         _dp.begin_step(batch)
         loss = self._get_loss_dict()
         if self.gan_flag:
@@ -43,9 +43,7 @@ class LSGANTrainer(VQVAETrainer):
             loss = self.forward_vqvae(batch, loss, phase=phase)
         loss = self.forward_spkradv(batch, loss, phase=phase)
         loss = self.forward_spkrclassifier(batch, loss, phase=phase)
-        loss_values = self._parse_loss(loss)
-        self._flush_writer(loss, phase)
-        return loss_values
+        return loss
 
     def forward_lsgan(self, batch, loss, phase="train"):
         order = ["G", "D"] if self.conf["train_first"] == "G" else ["D", "G"]

@@ -28,6 +28,14 @@ class VQVAETrainer(BaseTrainer):
 
     # ---- public steps --------------------------------------------------------------------------
     def train(self, batch, phase="train"):
+        loss = self._train_core(batch, phase)
+        loss_values = self._parse_loss(loss)
+        self._flush_writer(loss, phase)
+        return loss_values
+
+    def _train_core(self, batch, phase="train"):
+        """Everything of a step that runs on the device, no host synchronisation: returns the loss dict of 0-dim
+        tensors (`_parse_loss` fetches them with one copy).  This is the unit a CUDA graph captures (net/graph.py)."""
         _dp.begin_step(batch)
         loss = self._get_loss_dict()
         if self.cycle_flag:
@@ -36,9 +44,7 @@ class VQVAETrainer(BaseTrainer):
             loss = self.forward_vqvae(batch, loss, phase=phase)
         loss = self.forward_spkradv(batch, loss, phase=phase)
         loss = self.forward_spkrclassifier(batch, loss, phase=phase)
-        loss_values = self._parse_loss(loss)
-        self._flush_writer(loss, phase)
-        return loss_values
+        return loss
 
     @torch.no_grad()
     def dev(self, batch):

@@ -348,6 +348,13 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step_count):
            C.c_float(beta1), C.c_float(beta2), C.c_float(eps), int(step_count))
 
 
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, step_dev):
+    """Adam with the step counter in device memory (int64 tensor of one element, incremented by the call)."""
+    L.require_cuda(p, g, m, v, step_dev)
+    L.call("crk_adam_step_dev", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), C.c_float(lr),
+           C.c_float(beta1), C.c_float(beta2), C.c_float(eps), L.ptr(step_dev))
+
+
 def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None):
     """wav (B, n_samples) -> (B, n_frames, n_mels);  frames start at m*hop (no centring here)."""
     L.require_cuda(wav, window, mel_basis)

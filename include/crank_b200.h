@@ -239,6 +239,11 @@ int crk_ce_bwd(const float* logits, int ldl, const long long* labels, long long 
  * state: m, v same size as p; step_count is the 1-based step number AFTER this update. */
 int crk_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                   float beta2, float eps, int step_count, void* stream);
+/* Same update with the step count in DEVICE memory (*step_dev is incremented first, then used for the bias
+ * corrections): no per-step host value in the launch arguments, so the call can be captured in a CUDA graph and
+ * replayed (crank_b200/net/graph.py). */
+int crk_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                      float beta2, float eps, long long* step_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Log-mel front end (crank/net/module/mlfb.py:134-171 online; crank/feature/feature.py:126-145 offline):

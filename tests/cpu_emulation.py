@@ -181,6 +181,12 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step_count):
     p.addcdiv_(m, denom, value=-(lr / bc1))
 
 
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, step_dev):
+    """crk_adam_step_dev: the counter lives in a tensor and is incremented by the call."""
+    step_dev += 1
+    adam_step(p, g, m, v, lr, beta1, beta2, eps, int(step_dev.item()))
+
+
 @contextlib.contextmanager
 def emulated_ops():
     """Swap the product's op bindings for the CPU stand-ins; everything is restored on exit."""
@@ -191,11 +197,12 @@ def emulated_ops():
              (ops, "VQFn", ops.VQFn), (ops, "vq_ema_update", ops.vq_ema_update),
              (ops, "MaskedLossFn", ops.MaskedLossFn), (ops, "CrossEntropyFn", ops.CrossEntropyFn),
              (ops, "StftLossFn", ops.StftLossFn), (ops, "adam_step", ops.adam_step),
+             (ops, "adam_step_dev", ops.adam_step_dev),
              (lib, "require_cuda", lib.require_cuda)]
     models.WavenetFn, models.ConvstackFn = WavenetEmu, ConvstackEmu
     ops.VQFn, ops.vq_ema_update = VQEmu, vq_ema_update
     ops.MaskedLossFn, ops.CrossEntropyFn = MaskedLossEmu, CrossEntropyEmu
-    ops.StftLossFn, ops.adam_step = StftLossEmu, adam_step
+    ops.StftLossFn, ops.adam_step, ops.adam_step_dev = StftLossEmu, adam_step, adam_step_dev
     lib.require_cuda = lambda *a, **k: None
     try:
         yield

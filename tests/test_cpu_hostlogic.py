@@ -176,3 +176,28 @@ def test_conversion_conditioning_matches_live_reference():
         assert torch.allclose(out["decoded"], ref["decoded"], atol=1e-4, rtol=1e-4)
         for n in range(conf["n_vq_stacks"]):
             assert torch.equal(out["qidx"][n], ref["qidx"][n])
+
+
+def test_capturable_fused_adam_equals_default():
+    """FusedAdam(capturable=True) keeps the step count in a device tensor (crk_adam_step_dev, graph-capturable);
+    the update must be the one of the default host-counter path, step after step, incl. a late switch-over."""
+    from crank_b200.net.trainer.optim import FusedAdam
+
+    torch.manual_seed(0)
+    w0 = torch.randn(257)
+    grads = [torch.randn(257) for _ in range(4)]
+    with emulated_ops():
+        pa, pb = torch.nn.Parameter(w0.clone()), torch.nn.Parameter(w0.clone())
+        oa, ob = FusedAdam([pa], lr=2e-4), FusedAdam([pb], lr=2e-4, capturable=True)
+        for i, g in enumerate(grads):
+            pa.grad, pb.grad = g.clone(), g.clone()
+            oa.step()
+            ob.step()
+            assert torch.equal(pa, pb), i
+        assert int(ob.state[pb]["step_dev"].item()) == 4
+        # an optimizer that ran eagerly first and becomes capturable later continues from its host step count
+        oa.capturable = True
+        pa.grad, pb.grad = grads[0].clone(), grads[0].clone()
+        oa.step()
+        ob.step()
+        assert torch.equal(pa, pb) and int(oa.state[pa]["step_dev"].item()) == 5
