@@ -45,8 +45,8 @@ int crk_debug_tc_disable(int mask);
 /* debugging / A-B measurement: switch optional optimisations off (results are unchanged up to the
  * summation order of bias gradients): bit 1 programmatic dependent launch, 2 bias column sums fused into
  * the tensor-core wgrad kernel, 4 128-bit epilogue of the tensor-core conv kernel, 8 shared-memory raw tile
- * feeding the k taps of the tensor-core wgrad kernel (off: one global fetch per tap), 16 single-batch staging
- * of the tensor-core conv kernel's activation tile */
+ * feeding the k taps of the tensor-core wgrad kernel (off: one global fetch per tap).  Bit 4 also selects the
+ * generic (all-options) instance of the conv kernel instead of the 128-bit-only one. */
 int crk_debug_opt_disable(int mask);
 
 /* instrumentation: number of kernels the library has launched in this process; optional CUDA-event
