@@ -201,3 +201,85 @@ def test_capturable_fused_adam_equals_default():
         oa.step()
         ob.step()
         assert torch.equal(pa, pb) and int(oa.state[pa]["step_dev"].item()) == 5
+
+
+def test_graphed_step_control_flow_with_a_fake_capture(monkeypatch):
+    """net/graph.py (experimental, not yet run on hardware): warm-up count, capture-once-per-signature, static input
+    buffers, loss-vector assembly, with torch.cuda's graph objects replaced by a fake: "capturing" executes nothing
+    (the step body hands back the loss dict of the eager step that preceded it, like a real capture records without
+    running) and replay() re-runs the step on the static batch.  Values must equal plain trainer.train."""
+    import contextlib
+
+    from crank_b200.conf import vcc2020_conf
+    from crank_b200.net import graph as G
+    from crank_b200.net.trainer import TrainerWrapper, get_criterion, get_model, get_optimizer, get_scheduler
+    from crank_b200.synthetic import clone_batch, make_batch, spkr_dict
+
+    flag = {"capturing": False}
+
+    class FakeGraph:
+        closure = None
+
+        def replay(self):
+            self.closure()
+
+    class FakeStream:
+        def wait_stream(self, other): pass
+
+    @contextlib.contextmanager
+    def fake_capture(g):
+        flag["capturing"] = True
+        yield
+        flag["capturing"] = False
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: FakeStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", fake_capture)
+
+    conf = vcc2020_conf(trainer_type="lsgan", n_steps_gan_start=-1, discriminator_dropout=0.0)
+
+    def build():
+        torch.manual_seed(4)
+        m = get_model(conf, S, device="cpu")
+        opt = get_optimizer(conf, m)
+        t = TrainerWrapper("lsgan", model=m, optimizer=opt, criterion=get_criterion(conf),
+                           dataloader={"spkrs": spkr_dict(S)}, writer={"train": _W(), "dev": _W()},
+                           expdir="/tmp/crank_b200_graph", conf=conf, feat_conf=conf["feature"],
+                           scheduler=get_scheduler(conf, opt), scaler=None, resume=0, device="cpu", n_jobs=1)
+        t.tqdm.close()
+        return t
+
+    batches = [make_batch(2, 96, S, seed=40 + i, ragged=True) for i in range(6)]
+    with emulated_ops():
+        ref = build()
+        ref_vals = [ref.train(clone_batch(b), "train") for b in batches]
+        t = build()
+        step = G.GraphedTrainStep(t)
+        assert all(o.capturable for o in t.optimizer.values())
+        orig_core = t._train_core
+        last = {}
+
+        def core(batch, phase):
+            if not flag["capturing"]:
+                last["loss"] = orig_core(batch, phase)
+            return last["loss"]
+
+        t._train_core = core
+        vals = []
+        for i, b in enumerate(batches):
+            vals.append(step(clone_batch(b)))
+            if i == G.GraphedTrainStep.WARMUP:            # the capture call just happened: wire the fake replay
+                (graph, static, keys, packed, const), = step._graphs.values()
+
+                def replay_closure(static=static, keys=keys, packed=packed):
+                    loss = orig_core(static, "train")
+                    packed.copy_(torch.stack([loss[k].detach().reshape(()).float() for k in keys]))
+
+                graph.closure = replay_closure
+        assert len(step._graphs) == 1
+    for i, (a, b) in enumerate(zip(vals, ref_vals)):
+        for k in b:
+            assert abs(a[k] - b[k]) <= 3e-4 * max(abs(b[k]), 1e-3), (i, k, a[k], b[k])
