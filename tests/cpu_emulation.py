@@ -181,6 +181,17 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step_count):
     p.addcdiv_(m, denom, value=-(lr / bc1))
 
 
+def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None):
+    """crk_logmel_fwd: frames start at m*hop (no centring here), |rFFT(window * frame)| . mel_basis -> log10."""
+    wav = wav.float()
+    frames = wav.unfold(-1, n_fft, hop) * window                        # (B, M, n_fft)
+    mag = torch.fft.rfft(frames, dim=-1).abs()
+    out = torch.log10(torch.clamp(mag @ mel_basis, min=eps))
+    if mean is not None:
+        out = (out - mean) / std
+    return out
+
+
 def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, step_dev):
     """crk_adam_step_dev: the counter lives in a tensor and is incremented by the call."""
     step_dev += 1
@@ -197,12 +208,13 @@ def emulated_ops():
              (ops, "VQFn", ops.VQFn), (ops, "vq_ema_update", ops.vq_ema_update),
              (ops, "MaskedLossFn", ops.MaskedLossFn), (ops, "CrossEntropyFn", ops.CrossEntropyFn),
              (ops, "StftLossFn", ops.StftLossFn), (ops, "adam_step", ops.adam_step),
-             (ops, "adam_step_dev", ops.adam_step_dev),
+             (ops, "adam_step_dev", ops.adam_step_dev), (ops, "logmel", ops.logmel),
              (lib, "require_cuda", lib.require_cuda)]
     models.WavenetFn, models.ConvstackFn = WavenetEmu, ConvstackEmu
     ops.VQFn, ops.vq_ema_update = VQEmu, vq_ema_update
     ops.MaskedLossFn, ops.CrossEntropyFn = MaskedLossEmu, CrossEntropyEmu
     ops.StftLossFn, ops.adam_step, ops.adam_step_dev = StftLossEmu, adam_step, adam_step_dev
+    ops.logmel = logmel
     lib.require_cuda = lambda *a, **k: None
     try:
         yield

@@ -283,3 +283,24 @@ def test_graphed_step_control_flow_with_a_fake_capture(monkeypatch):
     for i, (a, b) in enumerate(zip(vals, ref_vals)):
         for k in b:
             assert abs(a[k] - b[k]) <= 3e-4 * max(abs(b[k]), 1e-3), (i, k, a[k], b[k])
+
+
+def test_offline_mlfb_extraction_wrapper_against_the_reference_fixture():
+    """crank_b200.feature.extract_mlfb (symmetric hann, centred reflect padding, Slaney basis) reproduces the mlfb the
+    reference stored for test/data/SF1_10001.wav (committed copy) -- host logic only: the log-mel kernel behind
+    ops.logmel is emulated here and verified on the GPU in tests/test_gpu_kernels.py."""
+    import os
+
+    from crank_b200.feature import extract_mlfb, symmetric_hann
+    from oracle import mel as omel
+
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_fixture_mlfb.npz"))
+    raw, ref = fx["raw_i16"].astype(np.float64) / 32768.0, fx["mlfb"]
+    assert np.abs(symmetric_hann(1024) - omel.hann(1024, periodic=False)).max() < 1e-15
+    with emulated_ops():
+        got = extract_mlfb(raw, fs=22050, device="cpu").numpy()
+        both = extract_mlfb(np.stack([raw, raw[::-1].copy()]), fs=22050, device="cpu")
+    assert got.shape == ref.shape == (1057, 80)
+    # fp32 against the float64 fixture; quiet bins sit near the eps floor where log10 amplifies rounding
+    assert np.abs(got - ref).max() < 2e-3 and np.abs(got - ref).mean() < 2e-5, (np.abs(got - ref).max(), np.abs(got - ref).mean())
+    assert both.shape == (2, 1057, 80) and torch.allclose(both[0], torch.from_numpy(got))

@@ -426,3 +426,18 @@ def test_logmel_matches_oracle_on_reference_wav_fixture():
                                   num_mels=80, fmin=80, fmax=7600)
     assert got.shape == o_per.shape
     assert np.abs(got - o_per).max() < 1e-3, np.abs(got - o_per).max()
+
+
+def test_offline_mlfb_extraction_matches_reference_fixture():
+    """crank_b200.feature.extract_mlfb on the device (symmetric hann, centred) against the mlfb the reference stored
+    for its own test wav (float64 offline pipeline; test/test_feature_pytorch.py allows 1e-3 at this boundary)."""
+    import os
+
+    from crank_b200.feature import extract_mlfb
+
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_fixture_mlfb.npz"))
+    raw, ref = fx["raw_i16"].astype(np.float64) / 32768.0, fx["mlfb"]
+    got = extract_mlfb(raw, fs=22050, device=_dev()).cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 2e-3, np.abs(got - ref).max()
+    assert np.abs(got - ref).mean() < 5e-5
