@@ -42,15 +42,16 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=T_FRAMES)
     ap.add_argument("--trainer", default="lsgan", choices=["vqvae", "lsgan", "cyclegan", "stargan"])
-    ap.add_argument("--cpu-batch", type=int, default=16, help="utterances of the bounded CPU sample")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="utterances per step of the CPU arms (0 = the same batch as the GPU arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
                     help="EXPERIMENTAL (not yet validated on hardware): replay the step from a whole-step CUDA graph "
                          "(crank_b200/net/graph.py); lsgan / vqvae trainers only")
-    ap.add_argument("--eager-gpu-baseline", action="store_true",
-                    help="also time the reference's own graph (the oracle port, stock PyTorch eager: cuDNN / cuBLAS) on "
-                         "this GPU at the bench batch -- SURVEY.md section 8d's 'reference GPU path' bar; reported as "
-                         "`torch_eager_gpu_baseline`, never part of value / e2e")
+    ap.add_argument("--no-eager-gpu-baseline", action="store_true",
+                    help="skip timing the reference's own graph (the oracle port under stock PyTorch eager: cuDNN / "
+                         "cuBLAS) on this GPU at the bench batch -- SURVEY.md section 8d's 'reference GPU path' bar, "
+                         "reported as `torch_eager_gpu_baseline`, never part of value / e2e")
     ap.add_argument("--precision", default=os.environ.get("CRANK_B200_PRECISION", "tf32x3"),
                     choices=["fp32", "tf32x3", "tf32"],
                     help="conv contraction arithmetic: fp32 CUDA cores, 3xTF32 tcgen05 (parity mode), TF32 tcgen05")
@@ -88,6 +89,8 @@ def cpu_reference_throughput(kind, batch_utts, frames, steps, warmup):
     from oracle import crank_port as cp
 
     conf = bench_conf(kind)
+    # all host cores, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     random.seed(1234)
     np.random.seed(1234)
     torch.manual_seed(1234)
@@ -103,13 +106,18 @@ def cpu_reference_throughput(kind, batch_utts, frames, steps, warmup):
     return batch_utts * frames * steps / dt, dt / steps, torch.get_num_threads()
 
 
-def eager_gpu_reference_throughput(kind, batch_utts, frames, steps, warmup, device):
+def eager_gpu_reference_throughput(kind, batch_utts, frames, steps, warmup, device, allow_tf32=False):
     """frames/s of the oracle port of the reference's trainer run by stock PyTorch eager ON THE GPU (device-timed).
-    A reported bar only: what the unmodified reference graph achieves on the same B200."""
+    A reported bar only: what the unmodified reference graph achieves on the same B200 (cuDNN / cuBLAS / cuFFT,
+    `cudnn.benchmark = True` as crank/bin/train.py:52-53 sets it).  allow_tf32=False is the reference's arithmetic."""
     import random
 
     import numpy as np
     import torch
+
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = bool(allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
 
     from crank_b200.synthetic import clone_batch, make_batch, to_device
     from oracle import crank_port as cp
@@ -223,7 +231,8 @@ def measured_peaks():
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    fps, sec, threads = cpu_reference_throughput(args.trainer, args.cpu_batch, args.frames, args.steps, args.warmup)
+    cpu_batch = args.cpu_batch or args.batch
+    fps, sec, threads = cpu_reference_throughput(args.trainer, cpu_batch, args.frames, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "mel-frames/sec VQVAE+LSGAN train step", "value": fps,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -231,10 +240,10 @@ def run_reference(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"VCC2020 mlfb_vqvae.yml trainer_type={args.trainer}, 14 speakers, "
                                f"{args.frames}-frame utterances", "trainer": args.trainer,
-                   "frames": args.frames, "sample_utts": args.cpu_batch},
+                   "batch_per_gpu": cpu_batch, "global_batch": cpu_batch, "frames": args.frames, "sample_utts": cpu_batch},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                          "cpu": cpu_model_name(),
-                         "sample": f"{args.cpu_batch} utts x {args.frames} frames per step, {args.steps} steps "
+                         "sample": f"{cpu_batch} utts x {args.frames} frames per step, {args.steps} steps "
                                    "(the reference's trainer = oracle/crank_port.py, bit-identical to "
                                    "crank.net.trainer on CPU, torch eager fp32)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -435,17 +444,22 @@ def run_b200(args, rank, local_rank, world):
             "data_path": data_path,
         }
         if not args.no_cpu_baseline and world == 1:
-            fps, sec, threads = cpu_reference_throughput(kind, args.cpu_batch, T, 3, 1)
+            cpu_batch = args.cpu_batch or B
+            fps, sec, threads = cpu_reference_throughput(kind, cpu_batch, T, 3, 1)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                     "cpu": cpu_model_name(),
-                                    "sample": f"{args.cpu_batch} utts x {T} frames per step, 1 warm-up + 3 timed steps"}
-        if args.eager_gpu_baseline and world == 1:
+                                    "sample": f"{cpu_batch} utts x {T} frames per step, 1 warm-up + 3 timed steps"}
+        if not args.no_eager_gpu_baseline and world == 1:
             try:
-                fps, sec = eager_gpu_reference_throughput(kind, B, T, 5, 3, dev)
+                fps, sec = eager_gpu_reference_throughput(kind, B, T, 5, 3, dev, allow_tf32=False)
+                fps_t, sec_t = eager_gpu_reference_throughput(kind, B, T, 5, 3, dev, allow_tf32=True)
                 line["torch_eager_gpu_baseline"] = {
                     "value": fps, "unit": "frames/s", "ms_per_step": sec * 1e3, "kind": "port",
+                    "tf32_allowed": {"value": fps_t, "ms_per_step": sec_t * 1e3},
+                    "speedup_of_this_repo": value / fps if fps else None,
                     "what": "oracle/crank_port.py (bit-identical to the reference trainers on CPU) executed by stock "
-                            "PyTorch eager on this GPU, fp32, same batch; 3 warm-up + 5 timed steps"}
+                            "PyTorch eager on this GPU (cudnn.benchmark on), fp32 with allow_tf32 off (the reference's "
+                            "arithmetic) and, separately, on; same batch; 3 warm-up + 5 timed steps each"}
             except Exception as err:     # the bar is optional: never lose the bench line over it
                 line["torch_eager_gpu_baseline"] = {"unavailable": repr(err)[:200]}
         print(json.dumps(line), flush=True)

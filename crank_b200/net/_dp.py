@@ -60,6 +60,12 @@ def active():
     return world_size() > 1
 
 
+def rank():
+    if _state["enabled"] and dist.is_initialized():
+        return dist.get_rank(_state["group"])
+    return 0
+
+
 def all_reduce_sum(t):
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_state["group"])
     return t

@@ -1,4 +1,4 @@
-"""Whole-step CUDA graph -- OPT-IN, written in round 1, NOT YET RUN ON HARDWARE.
+"""Whole-step CUDA graph -- opt-in (`bench.py --graph`).
 
 Why: a train step is ~900 kernel launches.  At the recipe's per-GPU batch on 8 GPUs (8 utterances x 500 frames) the
 device needs ~3 ms for them but the host needs ~12 ms to issue them (measured: `profiles/bench_r1b_b8.json`,
@@ -53,6 +53,15 @@ class GraphedTrainStep:
             for p in m.parameters():
                 torch.autograd.graph.increment_version(p)
 
+    def _drop_weight_caches(self):
+        # BEFORE a capture: forget every cached effective-weight buffer, so that each network's first use inside
+        # the capture records its weight-norm kernel into a graph-pool buffer.  Without this the captured kernels
+        # of the first G / D uses would read the buffer the preceding eager step filled, which no replay refreshes.
+        for m in self.trainer.model.values():
+            for sub in m.modules():
+                if hasattr(sub, "_weff_key"):
+                    sub._weff, sub._weff_key = None, None
+
     def __call__(self, batch):
         t = self.trainer
         if self._eager_steps < self.WARMUP:
@@ -67,13 +76,15 @@ class GraphedTrainStep:
             with torch.cuda.stream(side):                      # THIS call's step runs eagerly, on a side stream
                 eager_values = t._parse_loss(t._train_core(static, self.phase))     # (torch's capture warm-up rule)
             torch.cuda.current_stream().wait_stream(side)
+            self._drop_weight_caches()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 loss = t._train_core(static, self.phase)
                 keys = [k for k, v in loss.items() if isinstance(v, torch.Tensor)]
                 packed = torch.stack([loss[k].detach().reshape(()).float() for k in keys])
             const = {k: float(v) for k, v in loss.items() if not isinstance(v, torch.Tensor)}
-            self._graphs[sig] = (graph, static, keys, packed, const)
+            self._graphs = {sig: (graph, static, keys, packed, const)}     # a schedule / lr change evicts the old graph + pool
+            self._drop_weight_caches()
             self._invalidate_weight_caches()
             return eager_values                                 # the capture itself executed nothing
         graph, static, keys, packed, const = entry
@@ -91,4 +102,6 @@ class GraphedTrainStep:
         for k, v in zip(keys, _dp.average_loss_vector(packed.clone()).tolist()):
             values[k] = v
         t._last_loss_values = values
+        if hasattr(t, "_flush_writer"):
+            t._flush_writer({k: packed[i] for i, k in enumerate(keys)}, self.phase)
         return values

@@ -100,6 +100,8 @@ class BaseTrainer(object):
             self._run_eval(flag, tdir)
 
     def save_model(self):
+        if _dp.active() and _dp.rank() != 0:      # one writer per checkpoint file (replicas are identical)
+            return
         checkpoint = self.expdir / "checkpoint_{}steps.pkl".format(self.steps)
         state = {"steps": self.steps, "model": {"G": self.model["G"].state_dict()}}
         for m in ["SPKRADV", "D", "C"]:
@@ -165,6 +167,8 @@ class BaseTrainer(object):
                 logging.info("{}: {}".format(k, v))
 
     def _flush_writer(self, loss, phase):
+        if _dp.active() and _dp.rank() != 0:      # rank 0 owns the event log (the values are rank-averaged)
+            return
         if self.steps % self.conf["n_steps_print_loss"] == 0:
             values = getattr(self, "_last_loss_values", None) or self._parse_loss(loss)
             for k, v in loss.items():

@@ -48,7 +48,9 @@ class WavenetFn(torch.autograd.Function):
         y = torch.empty(B, T, cfg.out_ch, dtype=_f32, device=x.device)
         act = _empty(L.lib().crk_wavenet_act_floats(C.byref(cfg), B, T), x.device)
         # no input needs a gradient (torch.no_grad / inference): nothing is saved for backward
-        entry = "crk_wavenet_fwd" if any(ctx.needs_input_grad) else "crk_wavenet_infer"
+        # (needs_input_grad mirrors requires_grad whatever the grad mode: test the mode too)
+        entry = "crk_wavenet_fwd" if (torch.is_grad_enabled() and any(ctx.needs_input_grad)) else "crk_wavenet_infer"
+        WavenetFn.last_entry = entry
         L.call(entry, C.byref(cfg), L.ptr(weff), L.ptr(x), ldx, L.ptr(c), ldc,
                L.ptr(dropmul), L.ptr(y), cfg.out_ch, L.ptr(act), B, T)
         ctx.net = net
