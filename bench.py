@@ -294,9 +294,9 @@ def run_b200(args, rank, local_rank, world):
     dev_batch = to_device(host_batch, dev)
 
     run_step = trainer.train
-    if args.graph:
-        from crank_b200.net.graph import GraphedTrainStep
+    from crank_b200.net.graph import GraphedTrainStep
 
+    if args.graph:
         stepper = GraphedTrainStep(trainer)
         run_step = lambda b, phase: stepper(b)      # noqa: E731
 
@@ -329,7 +329,10 @@ def run_b200(args, rank, local_rank, world):
         sync_all()
         return ms, out
 
-    for _ in range(max(args.warmup, 3)):
+    # --graph: the first WARMUP calls run eagerly and the next one captures (an eager step on a side stream + the
+    # capture + instantiation, ~0.1-0.2 s): all of that belongs to the warm-up, the timed region only sees replays
+    n_warm = max(args.warmup, 3) + (GraphedTrainStep.WARMUP + 2 if args.graph else 0)
+    for _ in range(n_warm):
         step_resident()
     launches0 = L.lib().crk_launch_count()
     sampler = ClockSampler(local_rank)
@@ -338,6 +341,8 @@ def run_b200(args, rank, local_rank, world):
     ms, losses = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = L.lib().crk_launch_count() - launches0
+    for _ in range(2 if args.graph else 0):      # (the host-batch shapes equal the resident ones: same graph)
+        step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
     d2h = 4 * len([k for k in losses if k])
     frames_per_step = world * B * T

@@ -425,7 +425,15 @@ def test_logmel_matches_oracle_on_reference_wav_fixture():
     o_per = omel.logmelfilterbank(raw, 22050, fft_size=1024, hop_size=128, win_length=1024, window="hann",
                                   num_mels=80, fmin=80, fmax=7600)
     assert got.shape == o_per.shape
-    assert np.abs(got - o_per).max() < 1e-3, np.abs(got - o_per).max()
+    # north star: <= 1e-4 relative on mlfb tensors (max |diff| / max |ref|, the convention of tests/util.rel_err).
+    # An fp32 STFT pipeline reaches ~1e-5 here (torch CPU fp32 vs the float64 oracle: 1.2e-5; 6.5e-5 max abs).
+    err_abs = np.abs(got - o_per).max()
+    err_rel = err_abs / np.abs(o_per).max()
+    lin_rel = np.abs(10.0 ** got.astype(np.float64) - 10.0 ** o_per).max() / (10.0 ** o_per).max()
+    print(f"online log-mel vs float64 oracle: max abs {err_abs:.2e}, rel-to-max {err_rel:.2e}, linear-mel rel {lin_rel:.2e}")
+    assert err_rel <= 1e-4, err_rel
+    assert err_abs <= 3e-4, err_abs
+    assert lin_rel <= 1e-5, lin_rel
 
 
 def test_offline_mlfb_extraction_matches_reference_fixture():
@@ -440,5 +448,9 @@ def test_offline_mlfb_extraction_matches_reference_fixture():
     got = extract_mlfb(raw, fs=22050, device=_dev()).cpu().numpy()
     assert got.shape == ref.shape
     # fp32 on the device vs the float64 fixture; the wrong (periodic) window would be off by 2.5e-2
-    assert np.abs(got - ref).max() < 5e-3, np.abs(got - ref).max()
-    assert np.abs(got - ref).mean() < 5e-4
+    err_abs, err_mean = np.abs(got - ref).max(), np.abs(got - ref).mean()
+    err_rel = err_abs / np.abs(ref).max()
+    print(f"offline mlfb vs the reference's feats.h5: max abs {err_abs:.2e}, mean {err_mean:.2e}, rel-to-max {err_rel:.2e}")
+    assert err_rel <= 1e-4, err_rel          # north star tolerance on mlfb tensors
+    assert err_abs <= 3e-4, err_abs
+    assert err_mean <= 5e-6, err_mean
