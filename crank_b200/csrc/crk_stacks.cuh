@@ -8,6 +8,7 @@
 #include "crk_conv.cuh"
 #include "crk_resblock.cuh"
 #include "crk_resblock_tc.cuh"
+#include "crk_resblock_pt.cuh"
 #include "crk_conv_tc.cuh"
 #include "crk_wgrad_tc.cuh"
 
@@ -291,7 +292,11 @@ inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float*
             q.WosTc = weff + L.tab.d[L.out[l]].tc_off;
             q.WaTc = c->aux_ch > 0 ? weff + L.tab.d[L.aux[l]].tc_off : nullptr;
             q.KaPad = c->aux_ch > 0 ? L.tab.d[L.aux[l]].tc_kpad : 0;
-            if (mode == CRK_PREC_TF32X3) CRK_TRY(launch_resblock_fwd_tc<true>(q, s));
+            const bool split = mode == CRK_PREC_TF32X3;
+            if (!(opt_disable_mask() & 16) && resblock_fwd_pt_ok(q, split)) {       // persistent pipelined kernel (round 2)
+                if (split) CRK_TRY(launch_resblock_fwd_pt<true>(q, s));
+                else CRK_TRY(launch_resblock_fwd_pt<false>(q, s));
+            } else if (split) CRK_TRY(launch_resblock_fwd_tc<true>(q, s));
             else CRK_TRY(launch_resblock_fwd_tc<false>(q, s));
         }
     }

@@ -24,7 +24,9 @@ for _ in range(2):
     run()
 # launch indices inside one fwd+bwd:  fwd TC: blocks 0..7 (idx 3 = k5 dil 2); conv TC: fwd first(0) head(1,2), bwd: head dgrads(3,4),
 # then per layer dgrad...; wgrad TC: head(0,1) then per layer: Wos(2), conv(3), ...
-sel = {"resblock_fwd k5 d2": (1, 3, ["stageX", "gemm1+TMA", "epi1", "gemm2+TaSb", "epi2"], 6),
+PT = not (int(os.environ.get("CRANK_B200_OPT_DISABLE", "0")) & 16)     # persistent pipelined forward: worker-side stamps
+sel = {"resblock_fwd k5 d2": (1, 3, ["stage X0,X1", "wait G1(0)", "E1(0)", "wait G2(0)", "E2(0)", "remaining tiles"], 7) if PT else
+                             (1, 3, ["stageX", "gemm1+TMA", "epi1", "gemm2+TaSb", "epi2"], 6),
        "conv dgrad k5 (K128,N64)": (3, 5, ["stageA", "mma+TMA", "tmem->smem", "coalesced epilogue"], 5),
        "gate backward (K128,N64,k1)": (4, 3, ["stage dH,dS->GOS", "mma+TMA", "tmem->smem", "gate' epilogue"], 5),
        "wgrad conv k5": (2, 3, ["issue loads+wait", "store G,X0", "taps(tile0)", "other tiles", "wait last", "epilogue"], 7),
