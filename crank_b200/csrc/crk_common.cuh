@@ -69,7 +69,8 @@ inline int& tc_disable_mask() { static int m = 0; return m; }
 // debugging / A-B switches for optional optimisations (crk_debug_opt_mask):
 //   1 programmatic dependent launch off, 2 bias column sums fused into k_wgrad_tc off,
 //   4 k_conv_tc FAST instance (128-bit staging + epilogue) off -> GENERIC instance, 8 raw-tile k_wgrad_tc_raw off,
-//   16 persistent pipelined fused forward (k_resblock_fwd_pt) off -> k_resblock_fwd_tc
+//   16 persistent pipelined fused forward (k_resblock_fwd_pt) off -> k_resblock_fwd_tc,
+//   32 persistent pipelined conv / dgrad (k_conv_pt) off -> k_conv_tc
 inline int& opt_disable_mask() { static int m = 0; return m; }
 
 // ---- programmatic dependent launch (PDL) -----------------------------------------------------

@@ -544,6 +544,10 @@ inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
     return launch_check();
 }
 
+// persistent pipelined variant (crk_conv_pt.cuh, included after this header)
+template <bool SPLIT> inline cudaError_t launch_conv_pt(const ConvTcParams& q, cudaStream_t s);
+inline bool conv_pt_ok(const ConvTcParams& q, bool split);
+
 // precision-aware dispatch: tensor cores when enabled and the shape fits, else the fp32 kernel
 inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc, int kpad, int npad, cudaStream_t s) {
     const int mode = precision_mode();
@@ -560,6 +564,8 @@ inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc,
                           q.kshift >= 0 && q.nshift >= 0;
         q.g_dH = q.g_dS = q.g_TaSb = nullptr; q.g_DG = q.g_GOS = q.g_Z = nullptr;
         const bool split = mode == CRK_PREC_TF32X3;
+        if (fast && !(opt_disable_mask() & 32) && conv_pt_ok(q, split))
+            return split ? launch_conv_pt<true>(q, s) : launch_conv_pt<false>(q, s);
         if (conv_tc_ok(q, split)) {
             if (fast) return split ? launch_conv_tc_t<true, CRK_CONV_FAST>(q, s) : launch_conv_tc_t<false, CRK_CONV_FAST>(q, s);
             return split ? launch_conv_tc_t<true, CRK_CONV_GENERIC>(q, s) : launch_conv_tc_t<false, CRK_CONV_GENERIC>(q, s);

@@ -91,6 +91,20 @@ __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float (&v)[32
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 lanes x 32 columns: reg[4b + 2h + e], b = 0..3
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // the order in which weight half-blobs are consumed; producer and issuer enumerate the SAME program
 //   kind 0: conv tap j of tile `tile`;  1: aux 1x1 of tile `tile`;  2: [out|skip] of tile `tile` (GEMM2)
 //   h: half index -- SPLIT: 0 = lo blob (pass A_hi x B_lo), 1 = hi blob (passes A_lo x B_hi, A_hi x B_hi);  !SPLIT: hi
@@ -480,14 +494,14 @@ inline bool resblock_fwd_pt_ok(const ResFwdTcParams& q, bool split) {
     const int halo = (q.p.k - 1) * q.p.dil;
     if (halo > 16 || q.p.k < 1) return false;                    // X tile <= 144 rows = 9 float4 per worker
     if (q.p.Ca > 0 && (q.KaPad > 64 || (q.KaPad & 7))) return false;   // aux operand: 64 + 64 tensor-memory columns
-    return resblock_fwd_pt_smem(q.p.k, q.p.dil, split) <= 227 * 1024;
+    return resblock_fwd_pt_smem(q.p.k, q.p.dil, split) <= 225 * 1024;
 }
 
 template <bool SPLIT>
 inline cudaError_t launch_resblock_fwd_pt(const ResFwdTcParams& q, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_resblock_fwd_pt<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_resblock_fwd_pt<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }

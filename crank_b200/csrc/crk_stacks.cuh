@@ -10,6 +10,7 @@
 #include "crk_resblock_tc.cuh"
 #include "crk_resblock_pt.cuh"
 #include "crk_conv_tc.cuh"
+#include "crk_conv_pt.cuh"
 #include "crk_wgrad_tc.cuh"
 
 namespace crk {
