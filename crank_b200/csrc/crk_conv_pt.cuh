@@ -214,20 +214,36 @@ __global__ void __launch_bounds__(CRK_PT_THREADS, 1) k_conv_pt(const ConvTcParam
                 if (g + 2 < nsegs_total) { a_load(g + 2); a_store(g + 2); }
             }
             const int gl = i * nseg + nseg - 1;          // last segment: its completion == the tile's accumulator
+            // side inputs of the epilogue (residual gradient, dropout multiplier) fetched BEFORE the accumulator wait:
+            // slot s = (cg, half, bb, hr) of this thread; one round trip instead of one per 8-column block
+            const int ncol64 = (q.Npad + 63) >> 6;       // 64-column groups (1 for N <= 64)
+            float2 pmul[16], pres[16];
+            {
+#pragma unroll
+                for (int sidx = 0; sidx < 16; ++sidx) {
+                    const int half = sidx >> 3, bb = (sidx >> 1) & 3, hr = sidx & 1;
+                    const int r = wq * 32 + half * 16 + (lane >> 2) + 8 * hr;
+                    const int col = hh * 32 + 8 * bb + 2 * (lane & 3);
+                    pmul[sidx] = make_float2(1.f, 1.f); pres[sidx] = make_float2(0.f, 0.f);
+                    if (r < nlive && col < p.Cout) {
+                        const size_t row = row0 + r;
+                        if (p.mul_src) pmul[sidx] = __ldg(reinterpret_cast<const float2*>(p.mul_src + row * p.ldmul + col));
+                        if (p.R) pres[sidx] = __ldg(reinterpret_cast<const float2*>(p.R + row * p.ldr + col));
+                    }
+                }
+            }
             ok &= pt_wait(&bar_acc[i & 1], (i >> 1) & 1, &timeout_s);
             tc::tc_fence_after();
             if (i == 0) dbg_stamp(q.dbg, 2);
             const bool more = gl + 2 < nsegs_total;
             if (more) a_load(gl + 2);                    // in flight under the epilogue
 
-            // ---------------- epilogue: 16x256b fragments, 64 columns per load ----------------
-            // this warp: lane quarter wq; of the Npad/8 column blocks, those of half hh (blocks hh*4.. per 64-column group)
-            const int ncol64 = (q.Npad + 63) >> 6;       // 64-column groups (1 for N <= 64)
+            // ---------------- epilogue: 16x256b fragments, this warp's 32 of each group's 64 columns ----------------
             for (int cg = 0; cg < ncol64; ++cg) {
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int lane0 = wq * 32 + half * 16;
-                    float v[16];                                               // this warp's 32 of the group's 64 columns
+                    float v[16];
                     tmem_ld_16x256b_x4(tmem + ((uint32_t)lane0 << 16) + (i & 1) * 128 + cg * 64 + hh * 32, v);
 #pragma unroll
                     for (int bb = 0; bb < 4; ++bb) {
@@ -235,27 +251,23 @@ __global__ void __launch_bounds__(CRK_PT_THREADS, 1) k_conv_pt(const ConvTcParam
                         if (col >= p.Cout) continue;
                         float2 bia = make_float2(0.f, 0.f);
                         if (p.bias) bia = __ldg(reinterpret_cast<const float2*>(p.bias + col));
-                        float2 mulv[2], rv[2], dv[2], oldv[2];
-#pragma unroll
-                        for (int hr = 0; hr < 2; ++hr) {
-                            const int r = lane0 + (lane >> 2) + 8 * hr;
-                            mulv[hr] = make_float2(1.f, 1.f); rv[hr] = make_float2(0.f, 0.f);
-                            dv[hr] = make_float2(1.f, 1.f); oldv[hr] = make_float2(0.f, 0.f);
-                            if (r < nlive) {
-                                const size_t row = row0 + r;
-                                if (p.mul_src) mulv[hr] = __ldg(reinterpret_cast<const float2*>(p.mul_src + row * p.ldmul + col));
-                                if (p.R) rv[hr] = __ldg(reinterpret_cast<const float2*>(p.R + row * p.ldr + col));
-                                if (p.dact_src) dv[hr] = __ldg(reinterpret_cast<const float2*>(p.dact_src + row * p.lddact + col));
-                                if (p.accumulate) oldv[hr] = *reinterpret_cast<const float2*>(p.Y + row * p.ldy + col);
-                            }
-                        }
 #pragma unroll
                         for (int hr = 0; hr < 2; ++hr) {
                             const int r = lane0 + (lane >> 2) + 8 * hr;
                             if (r >= nlive) continue;
+                            const size_t row = row0 + r;
+                            const int sidx = half * 8 + bb * 2 + hr;
+                            float2 mulv = pmul[sidx], rv = pres[sidx];
+                            if (cg > 0) {                                   // (N > 64: not prefetched)
+                                mulv = p.mul_src ? __ldg(reinterpret_cast<const float2*>(p.mul_src + row * p.ldmul + col)) : make_float2(1.f, 1.f);
+                                rv = p.R ? __ldg(reinterpret_cast<const float2*>(p.R + row * p.ldr + col)) : make_float2(0.f, 0.f);
+                            }
+                            float2 dv = make_float2(1.f, 1.f), oldv = make_float2(0.f, 0.f);
+                            if (p.dact_src) dv = __ldg(reinterpret_cast<const float2*>(p.dact_src + row * p.lddact + col));
+                            if (p.accumulate) oldv = *reinterpret_cast<const float2*>(p.Y + row * p.ldy + col);
                             float y[2] = {v[4 * bb + 2 * hr], v[4 * bb + 2 * hr + 1]};
-                            const float b2[2] = {bia.x, bia.y}, m2[2] = {mulv[hr].x, mulv[hr].y}, r2[2] = {rv[hr].x, rv[hr].y};
-                            const float d2[2] = {dv[hr].x, dv[hr].y}, o2[2] = {oldv[hr].x, oldv[hr].y};
+                            const float b2[2] = {bia.x, bia.y}, m2[2] = {mulv.x, mulv.y}, r2[2] = {rv.x, rv.y};
+                            const float d2[2] = {dv.x, dv.y}, o2[2] = {oldv.x, oldv.y};
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 float t = y[e];                               // same operation order as k_conv / k_conv_tc
@@ -268,7 +280,7 @@ __global__ void __launch_bounds__(CRK_PT_THREADS, 1) k_conv_pt(const ConvTcParam
                                 t += o2[e];
                                 y[e] = t;
                             }
-                            *reinterpret_cast<float2*>(p.Y + (row0 + r) * p.ldy + col) = make_float2(y[0], y[1]);
+                            *reinterpret_cast<float2*>(p.Y + row * p.ldy + col) = make_float2(y[0], y[1]);
                         }
                     }
                 }

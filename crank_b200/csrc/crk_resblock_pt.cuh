@@ -406,6 +406,22 @@ __global__ void __launch_bounds__(CRK_PT_THREADS, 1) k_resblock_fwd_pt(const Res
             if (i + 1 < n_my) aux_stage(i + 1);          // acc1(i) complete => the aux MMAs of tile i have read the operand
 
             // ---------------- E2: (acc2 + bias) -> padded smem tile -> coalesced residual / skip pass ----------------
+            // The residual / old-skip rows this thread will combine are fetched BEFORE waiting for GEMM2 (they do not
+            // depend on it): the old loop issued 4 dependent load->store rounds per warp, ~2.4K cycles each under load.
+            // warp ww owns rows ww + 8j (j = 0..15), lane owns channels (2 lane, 2 lane + 1).
+            float2 res[16], sko[16];
+            {
+                const size_t base = row0 * 64;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int rr = ww + 8 * j;
+                    res[j] = make_float2(0.f, 0.f); sko[j] = make_float2(0.f, 0.f);
+                    if (rr < nlive) {
+                        res[j] = __ldg(reinterpret_cast<const float2*>(p.Hin + base + (size_t)rr * 64) + lane);
+                        if (!p.skip_init) sko[j] = *(reinterpret_cast<const float2*>(p.Skip + base + (size_t)rr * 64) + lane);
+                    }
+                }
+            }
             ok &= pt_wait(&bar_acc2, i & 1, &timeout_s);
             tc::tc_fence_after();
             if (i == 0) dbg_stamp(q.dbg, 4);
@@ -434,29 +450,18 @@ __global__ void __launch_bounds__(CRK_PT_THREADS, 1) k_resblock_fwd_pt(const Res
             pt_worker_sync();
             {
                 const size_t base = row0 * 64;
-                for (int rr0 = ww; rr0 < nlive; rr0 += 32) {
-                    float2 res[4], sko[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int rr = rr0 + 8 * u;
-                        if (rr < nlive) {
-                            res[u] = __ldg(reinterpret_cast<const float2*>(p.Hin + base + (size_t)rr * 64) + lane);
-                            if (!p.skip_init) sko[u] = *(reinterpret_cast<const float2*>(p.Skip + base + (size_t)rr * 64) + lane);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int rr = rr0 + 8 * u;
-                        if (rr >= nlive) continue;
-                        const float* sp = S2 + rr * SST + 4 * lane;
-                        float2 ho, sk;
-                        ho.x = (sp[0] + res[u].x) * CRK_SQRT_HALF;
-                        ho.y = (sp[1] + res[u].y) * CRK_SQRT_HALF;
-                        sk.x = sp[2]; sk.y = sp[3];
-                        if (!p.skip_init) { sk.x += sko[u].x; sk.y += sko[u].y; }
-                        reinterpret_cast<float2*>(p.Hout + base + (size_t)rr * 64)[lane] = ho;
-                        reinterpret_cast<float2*>(p.Skip + base + (size_t)rr * 64)[lane] = sk;
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    const int rr = ww + 8 * j;
+                    if (rr >= nlive) continue;
+                    const float* sp = S2 + rr * SST + 4 * lane;
+                    float2 ho, sk;
+                    ho.x = (sp[0] + res[j].x) * CRK_SQRT_HALF;
+                    ho.y = (sp[1] + res[j].y) * CRK_SQRT_HALF;
+                    sk.x = sp[2]; sk.y = sp[3];
+                    if (!p.skip_init) { sk.x += sko[j].x; sk.y += sko[j].y; }
+                    reinterpret_cast<float2*>(p.Hout + base + (size_t)rr * 64)[lane] = ho;
+                    reinterpret_cast<float2*>(p.Skip + base + (size_t)rr * 64)[lane] = sk;
                 }
             }
             pt_worker_sync();                            // S2 fully read before X(i+2) / z(i+2) overwrite the buffer

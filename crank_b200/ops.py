@@ -39,7 +39,7 @@ class WavenetFn(torch.autograd.Function):
     """One WaveNet stack (first 1x1, L gated residual blocks, head) -- crk_wavenet_fwd / _bwd."""
 
     @staticmethod
-    def forward(ctx, net, x, c, dropmul, theta):
+    def forward(ctx, net, x, c, dropmul, theta, save_gates=True):
         x, ldx = panel(x)
         c, ldc = panel(c)
         B, T, _ = x.shape
@@ -47,9 +47,10 @@ class WavenetFn(torch.autograd.Function):
         weff = net.effective_weights()
         y = torch.empty(B, T, cfg.out_ch, dtype=_f32, device=x.device)
         act = _empty(L.lib().crk_wavenet_act_floats(C.byref(cfg), B, T), x.device)
-        # no input needs a gradient (torch.no_grad / inference): nothing is saved for backward
-        # (needs_input_grad mirrors requires_grad whatever the grad mode: test the mode too)
-        entry = "crk_wavenet_fwd" if (torch.is_grad_enabled() and any(ctx.needs_input_grad)) else "crk_wavenet_infer"
+        # `save_gates` is decided by the CALLER (forward_cl): inside Function.forward grad mode is always off and
+        # needs_input_grad mirrors requires_grad whatever the caller's grad mode, so neither can tell a
+        # torch.no_grad() pass from a training pass.  False: inference entry, nothing is saved for backward.
+        entry = "crk_wavenet_fwd" if save_gates else "crk_wavenet_infer"
         WavenetFn.last_entry = entry
         L.call(entry, C.byref(cfg), L.ptr(weff), L.ptr(x), ldx, L.ptr(c), ldc,
                L.ptr(dropmul), L.ptr(y), cfg.out_ch, L.ptr(act), B, T)
@@ -86,7 +87,7 @@ class WavenetFn(torch.autograd.Function):
         L.call("crk_wavenet_bwd", C.byref(cfg), L.ptr(theta), L.ptr(weff), L.ptr(x), ldx,
                L.ptr(c), ldc, L.ptr(dropmul), L.ptr(act), L.ptr(dy), lddy,
                L.ptr(dx), cfg.in_ch, L.ptr(dc), max(cfg.aux_ch, 0), L.ptr(gtheta), L.ptr(ws), B, T)
-        return None, dx, dc, None, gtheta
+        return None, dx, dc, None, gtheta, None
 
 
 class ConvstackFn(torch.autograd.Function):

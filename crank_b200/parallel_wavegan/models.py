@@ -195,7 +195,10 @@ class _WavenetBase(_PackedConvNet):
             raise AssertionError("this stack was built with aux_channels > 0: `c` is required")
         if self.cfg.aux_ch == 0:
             c = None
-        return WavenetFn.apply(self, x, c, dropmul, self.theta)
+        # under torch.no_grad() (or when nothing upstream requires a gradient) the inference entry is used:
+        # the (tanh, sigmoid) pairs backward would need are not written (40 % of the block's output traffic)
+        needs = self.theta.requires_grad or x.requires_grad or (c is not None and c.requires_grad)
+        return WavenetFn.apply(self, x, c, dropmul, self.theta, bool(torch.is_grad_enabled() and needs))
 
     @property
     def receptive_field_size(self):

@@ -120,6 +120,63 @@ __global__ void __launch_bounds__(128) k_probe(P p) {
     if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
 
+
+// ---- T7: MN-major tf32 operands in the 128B-SWIZZLED layout (rows = frames, 32 channels = 128 B per row) ----------
+//   elem(frame f, channel c) at panel(c/32) + (f/8)*1024 + (f%8)*128 + (((c%32)/4) ^ (f%8))*16 + (c%4)*4
+//   descriptor: layout SWIZZLE_128B (2), LBO = panel stride (next 32 channels), SBO = 1024 (next 8 frames)
+struct PS { const float* A; const float* B; float* D; int K, N, rows_alloc, shiftA, shiftB, boff_mode; };
+__device__ void stage_sw(float* dst, const float* src, int rows, int cols, int rows_alloc) {
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+        const int f = i / cols, c = i % cols;
+        const int off = (c / 32) * rows_alloc * 32 + (f / 8) * 256 + (f % 8) * 32 + ((((c % 32) / 4) ^ (f % 8)) * 4) + (c % 4);
+        dst[off] = src[i];
+    }
+}
+__global__ void __launch_bounds__(128) k_probe_sw(PS p) {
+    extern __shared__ __align__(1024) float4 sm4[];
+    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm4) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rA = p.K + p.shiftA, rB = p.K + p.shiftB;
+    float* a = smem;
+    float* b = a + 4 * p.rows_alloc * 32;               // 4 panels of A (128 channels)
+    stage_sw(a, p.A, rA, 128, p.rows_alloc);
+    stage_sw(b, p.B, rB, p.N, p.rows_alloc);
+    if (threadIdx.x == 0) { tc::mbar_init(&mbar, 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc<128>(&tmem_base);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = tc::make_idesc_tf32(128, p.N, 1, 1);
+        const uint32_t pstride = p.rows_alloc * 128;
+        uint32_t acc = 0;
+        for (int k0 = 0; k0 < p.K; k0 += 8) {
+            const uint32_t sa = tc::smem_u32(a) + (k0 + p.shiftA) * 128, sb = tc::smem_u32(b) + (k0 + p.shiftB) * 128;
+            uint64_t da = tc::make_smem_desc(sa, pstride, 1024) | (2ull << 61);
+            uint64_t db = tc::make_smem_desc(sb, pstride, 1024) | (2ull << 61);
+            if (p.boff_mode == 1) { da |= (uint64_t)((sa >> 7) & 7) << 49; db |= (uint64_t)((sb >> 7) & 7) << 49; }
+            tc::umma_tf32(tmem, da, db, idesc, acc);
+            acc = 1;
+        }
+        tc::umma_commit(&mbar);
+    }
+    const bool ok = tc::mbar_wait(&mbar, 0);
+    tc::tc_fence_after();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < p.N; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        for (int i = 0; i < 32; ++i) p.D[row * p.N + c0 + i] = ok ? v[i] : NAN;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<128>(tmem);
+}
+
 // ---- T5: 16x256b fragment layout -----------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_frag(float* out /*[128 thr][16 regs][1]*/) {
     __shared__ uint32_t tmem_base;
@@ -288,6 +345,30 @@ int main(int argc, char** argv) {
             run(p, Acut, Bcut, 0, p.a_mn ? 128 : K, 0, p.b_mn ? N : K);
             std::vector<double> R; ref_fm(N, 0, p.shiftB, 128, R);
             printf("T1 N=%3d rows_alloc=%2d variant=%d a_mn=%d b_mn=%d shiftB=%d  relerr=%.3e\n", N, ralloc, variant, p.a_mn, p.b_mn, p.shiftB, relerr(R, N));
+        }
+    }
+
+
+    if (want("T7")) {
+        printf("== T7: MN-major tf32, SWIZZLE_128B (rows = frames).  err<3e-3 means it works\n");
+        CK(cudaFuncSetAttribute(k_probe_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (int N : {64, 128}) for (int boff = 0; boff < 2; ++boff) for (int sa : {0, 8}) for (int sb : {0, 1, 3, 8}) {
+            std::vector<float> Bsrc((K + 8) * N);
+            for (int f = 0; f < K + 8; ++f) for (int n = 0; n < N; ++n) Bsrc[f * N + n] = Bfn[f * 128 + n];
+            CK(cudaMemcpy(dA, Afm.data(), Afm.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(dB, Bsrc.data(), Bsrc.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemset(dD, 0xff, M * N * 4));
+            PS ps = {dA, dB, dD, K, N, 72, sa, sb, boff};
+            k_probe_sw<<<1, 128, (4 + N / 32) * 72 * 128 + 2048>>>(ps);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("  kernel error: %s\n", cudaGetErrorString(e)); exit(2); }
+            CK(cudaMemcpy(D.data(), dD, M * N * 4, cudaMemcpyDeviceToHost));
+            std::vector<double> R(M * N, 0.0);
+            for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
+                double sum = 0; for (int f = 0; f < K; ++f) sum += (double)Afm[(f + sa) * M + m] * Bfn[(f + sb) * 128 + n];
+                R[m * N + n] = sum;
+            }
+            printf("T7 N=%3d base_offset_mode=%d shiftA=%d shiftB=%d relerr=%.3e\n", N, boff, sa, sb, relerr(R, N));
         }
     }
 

@@ -34,7 +34,7 @@ class WavenetEmu:
     """crk_wavenet_fwd / _bwd (autograd supplies the backward)."""
 
     @staticmethod
-    def apply(net, x, c, dropmul, theta):
+    def apply(net, x, c, dropmul, theta, save_gates=True):
         cfg = net.cfg
         W = _views(net, theta)
         B, T, _ = x.shape

@@ -232,10 +232,19 @@ def test_no_grad_forward_and_skipped_final_decoder_are_invisible():
     x = torch.randn(B, T, 80, device="cuda")
     dec_h = torch.randn(B, T, 2, device="cuda")
     spk = torch.randint(0, 4, (B, 1), device="cuda").expand(B, T).contiguous()
+    from crank_b200.ops import WavenetFn
+
     oa = Ga.forward(x, None, dec_h, spkrvec=spk)
+    assert WavenetFn.last_entry == "crk_wavenet_fwd"          # training pass: gates saved for backward
     with torch.no_grad():
         ob = Gb.forward(x, None, dec_h, spkrvec=spk)
+        assert WavenetFn.last_entry == "crk_wavenet_infer"    # the inference entry is really taken under no_grad
         oc = Gc.forward(x, None, dec_h, spkrvec=spk, final_decoder=False)
+    # and a backward through the training pass still sees its saved gates (regression: the entry must not be chosen
+    # from the grad mode INSIDE Function.forward, where it is always off)
+    oa["decoded"].square().mean().backward()
+    assert Ga.decoders[0].theta.grad is not None and Ga.decoders[0].theta.grad.abs().max().item() > 0
+    assert Ga.encoders[1].theta.grad.abs().max().item() > 0
     assert torch.equal(oa["decoded"], ob["decoded"])
     assert oc["decoded"] is None
     for n in range(conf["n_vq_stacks"]):
