@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=T_FRAMES)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="STRONG scaling: total utterances per step, split evenly over the ranks (BASELINE config 3 is "
+                         "--global-batch 64: 8 utterances per GPU at N=8); default 0 = weak scaling with --batch per GPU")
     ap.add_argument("--trainer", default="lsgan", choices=["vqvae", "lsgan", "cyclegan", "stargan"])
     ap.add_argument("--cpu-batch", type=int, default=0,
                     help="utterances per step of the CPU arms (0 = the same batch as the GPU arm)")
@@ -285,6 +288,10 @@ def run_b200(args, rank, local_rank, world):
                              conf=conf, feat_conf=conf["feature"], scheduler=get_scheduler(conf, opt),
                              scaler=None, resume=0, device=dev, n_jobs=1)
     trainer.tqdm.close()
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        args.batch = args.global_batch // world
     B, T = args.batch, args.frames
     host_batch = make_batch(B, T, N_SPKRS, seed=1000 + rank)     # each rank its own utterances
     for k, v in host_batch.items():
@@ -414,7 +421,7 @@ def run_b200(args, rank, local_rank, world):
         line = {
             "metric": "mel-frames/sec VQVAE+LSGAN train step", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32)", "tf32": "tf32"}[args.precision],
+            "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32)", "tf32": "tf32"}[args.precision],
             "data": "synthetic",
             "config": {
                 "workload": f"VCC2020 conf/mlfb_vqvae.yml trainer_type={kind} (GAN phase), {B} utts/GPU x {T} "

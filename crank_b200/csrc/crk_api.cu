@@ -54,6 +54,7 @@ int crk_set_precision(int mode) {
 int crk_get_precision(void) { return precision_mode(); }
 int crk_debug_tc_disable(int mask) { tc_disable_mask() = mask; return CRK_OK; }
 int crk_debug_opt_disable(int mask) { opt_disable_mask() = mask; return CRK_OK; }
+int crk_debug_opt_enable(int mask) { opt_enable_mask() = mask; return CRK_OK; }
 int crk_debug_timestamps(long long* device_buffer, int kernel_id, int launch_index) {
     API_TRY(cudaMemcpyToSymbol(g_crk_dbg, &device_buffer, sizeof(device_buffer)));
     DbgSel& d = dbg_sel();

@@ -72,6 +72,10 @@ inline int& tc_disable_mask() { static int m = 0; return m; }
 //   16 persistent pipelined fused forward (k_resblock_fwd_pt) off -> k_resblock_fwd_tc,
 //   32 persistent pipelined conv / dgrad (k_conv_pt) off -> k_conv_tc
 inline int& opt_disable_mask() { static int m = 0; return m; }
+// opt-IN switches (crk_debug_opt_enable / CRANK_B200_OPT_ENABLE): experimental paths that are correct (parity-tested)
+// but not yet faster than the default ones:
+//   1 persistent pipelined fused forward k_resblock_fwd_pt, 2 persistent pipelined conv / dgrad k_conv_pt
+inline int& opt_enable_mask() { static int m = 0; return m; }
 
 // ---- programmatic dependent launch (PDL) -----------------------------------------------------
 // The steps of a stack are hundreds of short dependent kernels on one stream.  A kernel launched with

@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(CRK_PT_THREADS, 1) k_conv_pt(const ConvTcParam
             if (i == 0) dbg_stamp(q.dbg, 2);
             const bool more = gl + 2 < nsegs_total;
             if (more) a_load(gl + 2);                    // in flight under the epilogue
+            if (i == 0) dbg_stamp(q.dbg, 5);
 
             // ---------------- epilogue: 16x256b fragments, this warp's 32 of each group's 64 columns ----------------
             for (int cg = 0; cg < ncol64; ++cg) {
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(CRK_PT_THREADS, 1) k_conv_pt(const ConvTcParam
                 }
             }
             tc::tc_fence_before();
+            if (i == 0) dbg_stamp(q.dbg, 6);
             if (more) a_store(gl + 2);
             if (i == 0) dbg_stamp(q.dbg, 3);
         }

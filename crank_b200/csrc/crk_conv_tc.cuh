@@ -564,7 +564,7 @@ inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc,
                           q.kshift >= 0 && q.nshift >= 0;
         q.g_dH = q.g_dS = q.g_TaSb = nullptr; q.g_DG = q.g_GOS = q.g_Z = nullptr;
         const bool split = mode == CRK_PREC_TF32X3;
-        if (fast && !(opt_disable_mask() & 32) && conv_pt_ok(q, split))
+        if (fast && (opt_enable_mask() & 2) && conv_pt_ok(q, split))
             return split ? launch_conv_pt<true>(q, s) : launch_conv_pt<false>(q, s);
         if (conv_tc_ok(q, split)) {
             if (fast) return split ? launch_conv_tc_t<true, CRK_CONV_FAST>(q, s) : launch_conv_tc_t<false, CRK_CONV_FAST>(q, s);

@@ -294,7 +294,7 @@ inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float*
             q.WaTc = c->aux_ch > 0 ? weff + L.tab.d[L.aux[l]].tc_off : nullptr;
             q.KaPad = c->aux_ch > 0 ? L.tab.d[L.aux[l]].tc_kpad : 0;
             const bool split = mode == CRK_PREC_TF32X3;
-            if (!(opt_disable_mask() & 16) && resblock_fwd_pt_ok(q, split)) {       // persistent pipelined kernel (round 2)
+            if ((opt_enable_mask() & 1) && resblock_fwd_pt_ok(q, split)) {       // persistent pipelined kernel (round 2)
                 if (split) CRK_TRY(launch_resblock_fwd_pt<true>(q, s));
                 else CRK_TRY(launch_resblock_fwd_pt<false>(q, s));
             } else if (split) CRK_TRY(launch_resblock_fwd_tc<true>(q, s));

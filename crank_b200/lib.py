@@ -56,6 +56,7 @@ SIGNATURES = {
     "crk_get_precision": (i32, []),
     "crk_debug_tc_disable": (i32, [i32]),
     "crk_debug_opt_disable": (i32, [i32]),
+    "crk_debug_opt_enable": (i32, [i32]),
     "crk_debug_timestamps": (i32, [vp, i32, i32]),
     "crk_launch_count": (C.c_ulonglong, []),
     "crk_timing_enable": (i32, [i32]),
@@ -127,6 +128,7 @@ def lib():
         handle.crk_set_precision(PRECISIONS[mode])
         # A/B switch for optional optimisations (see crk_debug_opt_disable in include/crank_b200.h)
         handle.crk_debug_opt_disable(int(os.environ.get("CRANK_B200_OPT_DISABLE", "0")))
+        handle.crk_debug_opt_enable(int(os.environ.get("CRANK_B200_OPT_ENABLE", "0")))
     return _lib
 
 

@@ -48,6 +48,9 @@ int crk_debug_tc_disable(int mask);
  * feeding the k taps of the tensor-core wgrad kernel (off: one global fetch per tap).  Bit 4 also selects the
  * generic (all-options) instance of the conv kernel instead of the 128-bit-only one. */
 int crk_debug_opt_disable(int mask);
+/* opt-in experimental paths (parity-tested, not yet faster than the defaults): bit 1 persistent
+ * warp-specialised fused residual-block forward (k_resblock_fwd_pt), 2 persistent pipelined conv / dgrad (k_conv_pt) */
+int crk_debug_opt_enable(int mask);
 
 /* instrumentation: number of kernels the library has launched in this process; optional CUDA-event
  * timing of one kernel family (ids: 1 resblock_fwd, 2 wgrad, 3 conv, 4 resblock_bwd_gate, 5 vq_argmin;

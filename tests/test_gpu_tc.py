@@ -196,3 +196,19 @@ def test_tc_vq_argmin_is_identical_to_fp32_kernel(precision):
         nm = int((i0 != i1).sum())
         assert nm == 0, f"{kind}: {nm} indices differ between the fp32 and the tensor-core argmin"
         assert torch.equal(e0, e1) and torch.equal(q0, q1)
+
+
+@pytest.mark.parametrize("in_ch,out_ch,aux,k,layers,stacks,causal,B,T", [_STACKS[0], _STACKS[2], _STACKS[3], _STACKS[5]])
+def test_persistent_pipelined_kernels_opt_in_path(precision, in_ch, out_ch, aux, k, layers, stacks, causal, B, T):
+    """The opt-in persistent warp-specialised kernels (k_resblock_fwd_pt: overlapped GEMM / gate / epilogue with the aux
+    operand in tensor memory; k_conv_pt: segment-pipelined dgrad with 16x256b epilogues) against the oracle: forward,
+    input / conditioning gradients and every parameter gradient at the same 1e-4 as the default kernels."""
+    from crank_b200 import lib as L
+    from tests import test_gpu_kernels as tk
+
+    L.check(L.lib().crk_debug_opt_enable(3), "opt_enable")
+    try:
+        precision("tf32x3")
+        tk.test_wavenet_stack_fwd_bwd(in_ch, out_ch, aux, k, layers, stacks, causal, B, T)
+    finally:
+        L.check(L.lib().crk_debug_opt_enable(0), "opt_enable")
