@@ -59,6 +59,7 @@ class VQVAE2(nn.Module):
         decoder stack, whose output no quantiser consumes: used by the speaker-adversarial update, which only reads
         the encoder outputs of this pass but must keep its EMA codebook updates (trainer_vqvae.py:165-180).
         "decoded" is then None."""
+        self._dp_wait()
         x = self._pre(x)
         dec_h = self._get_dec_h(dec_h, spkrvec)
         enc = self.encode(x, enc_h=enc_h)
@@ -67,7 +68,14 @@ class VQVAE2(nn.Module):
                                                    final_decoder=final_decoder)
         return self.make_dict(enc, dec, emb_idxs, qidxs, enc_unmod)
 
+    def _dp_wait(self):
+        # data parallel: a side-stream gradient all-reduce + Adam step (or EMA codebook update) of this generator may
+        # still be in flight: the compute stream waits for it before the parameters / codebooks are read
+        if _dp.active():
+            _dp.wait_for(list(self.parameters()) + list(self.buffers()))
+
     def cycle_forward(self, x, org_enc_h, org_dec_h, cv_enc_h, cv_dec_h, org_spkrvec, cv_spkrvec):
+        self._dp_wait()
         x = self._pre(x)
         org_dec_h = self._get_dec_h(org_dec_h, org_spkrvec)
         cv_dec_h = self._get_dec_h(cv_dec_h, cv_spkrvec)
@@ -196,11 +204,17 @@ class Quantizer(nn.Module):
 
     def forward_cl(self, x, use_ema=True):
         W = self.embedding.weight
+        if _dp.active():
+            _dp.wait_for([W] + ([self.ema_size, self.ema_w] if self.ema_flag else []))
         e, qx, idx = ops.VQFn.apply(x, W if not self.ema_flag else W.detach())
         if self.training and self.ema_flag and use_ema:
             with torch.no_grad():
+                # data parallel: the [counts | sums] all-reduce and the EMA kernels that follow it go to the
+                # communication stream; this quantiser's NEXT call (the only reader of the new codebook) waits for them
+                keys = (W, self.ema_size, self.ema_w)
                 ops.vq_ema_update(x.detach(), idx, self.ema_size, self.ema_w, W.data, self.decay,
-                                  self.eps, reduce_fn=_dp.stats_reducer())
+                                  self.eps, reduce_fn=_dp.stats_reducer(),
+                                  runner=(lambda fn, stats: _dp.run_async(keys, fn, tensors=(stats,))) if _dp.active() else None)
         return e, qx, idx
 
     def vq(self, x):

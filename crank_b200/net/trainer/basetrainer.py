@@ -100,6 +100,7 @@ class BaseTrainer(object):
             self._run_eval(flag, tdir)
 
     def save_model(self):
+        _dp.flush()
         if _dp.active() and _dp.rank() != 0:      # one writer per checkpoint file (replicas are identical)
             return
         checkpoint = self.expdir / "checkpoint_{}steps.pkl".format(self.steps)
@@ -206,11 +207,16 @@ class BaseTrainer(object):
         self.optimizer[model].zero_grad()
         loss[model].backward()
         params = [p for p in self.model[model].parameters()]
-        _dp.average_gradients(params)
         clip = self.conf["optim"][model]["clip_grad_norm"]
-        if clip != 0:
-            torch.nn.utils.clip_grad_norm_(params, clip)
-        self.optimizer[model].step()
+
+        def reduce_and_update():
+            _dp.average_gradients(params)
+            if clip != 0:
+                torch.nn.utils.clip_grad_norm_(params, clip)
+            self.optimizer[model].step()
+
+        # data parallel: on the communication stream (the next reader of these parameters waits for it)
+        _dp.run_async(params, reduce_and_update)
 
     # ---- conditioning vectors (basetrainer.py:253-309) -----------------------------------------
     def _get_enc_h(self, batch, use_cvfeats=False, cv_spkr_name=None):

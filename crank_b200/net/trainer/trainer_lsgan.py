@@ -140,5 +140,6 @@ class LSGANTrainer(VQVAETrainer):
             else:
                 h = batch[f"{label}_h"]
                 h = h[:, 0:1].expand_as(h)  # drop the ignore_index padding
+                _dp.wait_for((self.model["G"].spkr_embedding.weight,))
                 parts.append(self.model["G"].spkr_embedding(h).detach())
         return torch.cat(parts, dim=-1).float()

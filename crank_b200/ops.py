@@ -172,9 +172,10 @@ class VQFn(torch.autograd.Function):
         return gx, gW
 
 
-def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None):
+def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None, runner=None):
     """EMA codebook update (vqvae2.py:315-330).  `reduce_fn(flat_stats)` sums [counts | esum]
-    across data-parallel ranks before the normalisation."""
+    across data-parallel ranks before the normalisation; `runner(fn, stats)` may run
+    that reduction and the EMA kernels somewhere else (the communication stream) instead of inline."""
     x, ldx = panel(x)
     B, T, D = x.shape
     K = W.shape[0]
@@ -185,10 +186,16 @@ def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None):
     esum = stats[K:]
     L.call("crk_vq_stats", L.ptr(x), ldx, L.ptr(idx), L.ptr(counts), L.ptr(esum), L.ptr(ws),
            B * T, K, D)
-    if reduce_fn is not None:
-        reduce_fn(stats)
-    L.call("crk_vq_ema", L.ptr(counts), L.ptr(esum), L.ptr(ema_size), L.ptr(ema_w), L.ptr(W),
-           C.c_float(decay), C.c_float(eps), K, D)
+    def finish():
+        if reduce_fn is not None:
+            reduce_fn(stats)
+        L.call("crk_vq_ema", L.ptr(counts), L.ptr(esum), L.ptr(ema_size), L.ptr(ema_w), L.ptr(W),
+               C.c_float(decay), C.c_float(eps), K, D)
+
+    if runner is not None:
+        runner(finish, stats)
+    else:
+        finish()
 
 
 # ---------------------------------------------------------------------------------------------

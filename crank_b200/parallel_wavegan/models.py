@@ -26,6 +26,7 @@ from collections import OrderedDict
 import torch
 
 from .. import lib as L
+from ..net import _dp
 from ..ops import ConvstackFn, WavenetFn
 
 _ACT = {"none": 0, "ReLU": 1, "LeakyReLU": 2}
@@ -64,6 +65,7 @@ class _PackedConvNet(torch.nn.Module):
 
     def effective_weights(self):
         th = self.theta
+        _dp.wait_for((th,))              # data parallel: a pending side-stream all-reduce + Adam of this pack
         key = (th._version, th.data_ptr())
         if self._weff is None or self._weff_key != key:
             L.require_cuda(th)
@@ -82,6 +84,7 @@ class _PackedConvNet(torch.nn.Module):
             yield name, g, v, b
 
     def _save_to_state_dict(self, destination, prefix, keep_vars):
+        _dp.flush()
         for name, g, v, b in self._conv_views():
             if b is not None:
                 destination[prefix + name + ".bias"] = b.clone()

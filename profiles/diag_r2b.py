@@ -13,6 +13,11 @@ ragged = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
 kind, S = "vqvae", 12
 conf, om, pm, O, P = _pair(kind, S)
 batch = make_batch(B, T, S, seed=0, ragged=ragged)
+warm = make_batch(B, T, S, seed=7, ragged=ragged)
+with torch.no_grad():
+    dh_, sp_ = O._dec_h(clone_batch(warm))
+    for _ in range(3):
+        om["G"].forward(warm["in_feats"], None, dh_, spkrvec=sp_)
 for k in om:
     pm[k].load_state_dict(om[k].state_dict())
 
@@ -35,7 +40,7 @@ def grads(mods):
     return out
 
 
-terms = ["G_l1", "G_stft", "G_commit0", "G_commit1", "G_spkradv_org", "G"]
+terms = ["G_l1", "G_mse", "G_stft", "G_commit0", "G_commit1", "G_spkradv_org", "G"]
 for term in terms:
     res = []
     for side in ("oracle", "product"):
@@ -63,8 +68,9 @@ for term in terms:
             loss[term].backward()
             for k in pm:
                 pm[k].load_state_dict(sd[k])
-        res.append((float(loss[term]), grads(mods)))
-    (lo, go), (lp, gp) = res
+        res.append((float(loss[term]), grads(mods), [q.detach().cpu().clone() for q in o["qidx"]]))
+    (lo, go, qo), (lp, gp, qp) = res
+    print("   qidx mismatches:", [int((a != b).sum()) for a, b in zip(qo, qp)])
     rows = sorted(((rel_err(gp[k], go[k]) if go[k].abs().max() > 0 else float(gp[k].abs().max()), k, float(go[k].abs().max()), float(gp[k].abs().max()))
                    for k in go if k in gp), reverse=True)
     missing = [k for k in go if k not in gp]

@@ -115,7 +115,7 @@ class VQEmu:
         return e, qx, idx
 
 
-def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None):
+def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None, runner=None):
     K, D = W.shape
     onehot = F.one_hot(idx.reshape(-1), K).float()
     stats = torch.cat([onehot.sum(0), (x.reshape(-1, D).T @ onehot).reshape(-1)])
