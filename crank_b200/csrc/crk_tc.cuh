@@ -199,10 +199,23 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __host__ __device__ constexpr int chunk_rows(int rows) { return (rows & 1) ? rows : rows + 1; }
 __host__ __device__ constexpr int chunk_stride_bytes(int rows) { return chunk_rows(rows) * 16; }
 
-// split x into a tf32-representable high part and the fp32 remainder (3xTF32 error compensation)
+// split x into two tf32-representable parts (3xTF32 error compensation), BOTH rounded to nearest:
+//   hi = rn_tf32(x)            |x - hi| <= 2^-12 |x|, exact difference in fp32
+//   lo = rn_tf32(x - hi)       |x - hi - lo| <= 2^-12 |x - hi| <= 2^-24 |x|
+// so hi + lo carries x to fp32's own precision and the dropped lo*lo term of a product is <= 2^-24 of it.
+// Round 1 truncated instead (hi = x & 0xFFFFE000, lo = x - hi left for the tensor core to truncate to 11 bits):
+// a one-sided error of up to 2^-21 |x| per operand, 8x larger -- measured as 5e-6 forward error per stack, enough to
+// flip ReLU derivatives of near-zero pre-activations in backward ~10x more often than the fp32 kernels do
+// (profiles/diag_r2c.py).  The tensor core truncates its fp32 operands to tf32 (profiles/hwprobe T4), which is exact
+// for values that are already tf32-representable.
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = x - hi;
+    hi = rn_tf32(x);
+    lo = rn_tf32(x - hi);
 }
 
 }  // namespace tc

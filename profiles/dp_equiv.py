@@ -104,7 +104,7 @@ def main():
                 worst_buf = max(worst_buf, (((dp_state[k] - v).abs().max() / v.abs().max().clamp_min(1e-30)).item(), k))
             else:
                 worst_rms = max(worst_rms, (rms, k))
-        ok = worst_loss[0] <= 1e-4 and worst_rms[0] <= 3e-2 and worst_buf[0] <= 1e-4
+        ok = worst_loss[0] <= 1e-4 and worst_rms[0] <= 3e-2 and worst_buf[0] <= 1e-3
         out = {"what": f"{world} ranks x {b} utterances == 1 device x {world * b} utterances, {kind}, T={T}, ragged masks, "
                        f"{STEPS} steps, 3xTF32 kernels, side-stream overlap {'on' if _dp._state['overlap'] else 'off'}",
                "worst_loss_rel_err": worst_loss, "worst_parameter_movement_rms_err": worst_rms,
