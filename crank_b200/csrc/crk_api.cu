@@ -10,6 +10,7 @@
 #include "crk_common.cuh"
 #include "crk_conv.cuh"
 #include "crk_loss.cuh"
+#include "crk_logmel.cuh"
 #include "crk_resblock.cuh"
 #include "crk_stacks.cuh"
 #include "crk_tc_probe.cuh"
@@ -574,6 +575,32 @@ int crk_logmel_fwd(const float* wav, int B, long long n_samples, const float* wi
     if (cufftSetStream(it->second, s) != CUFFT_SUCCESS) return CRK_ERR_CUDA;
     if (cufftExecR2C(it->second, frames, reinterpret_cast<cufftComplex*>(spec)) != CUFFT_SUCCESS) return CRK_ERR_CUDA;
     k_mel<<<(unsigned)cdivl(F, 64), CRK_THREADS, 0, s>>>(spec, bins, mel_basis, n_mels, eps, mean, stdv, F, out);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+
+
+// fused front end (crk_logmel.cuh): n_fft = 1024, banded mel projection.  `band_*`: for mel channel m the bins
+// [band_start[m], band_start[m] + band_len[m]) carry its non-zero weights band_w[band_off[m] ...].
+int crk_logmel_fused_fwd(const float* wav, int B, long long n_samples, const float* window, const int* band_start,
+                         const int* band_len, const int* band_off, const float* band_w, int nnz, int n_fft, int hop,
+                         int n_mels, float eps, const float* mean, const float* stdv, float* out, void* stream) {
+    if (!wav || !window || !band_start || !band_len || !band_off || !band_w || !out || B < 1 || hop < 1) return CRK_ERR_ARG;
+    if (n_fft != 1024 || n_mels < 1 || n_mels > 128 || nnz < 1 || nnz > CRK_MEL_MAXNNZ || hop > 512) return CRK_ERR_UNSUPPORTED;
+    if (n_samples < n_fft) return CRK_ERR_ARG;
+    LogmelParams p;
+    p.wav = wav; p.n_samples = n_samples; p.window = window; p.band_start = band_start; p.band_len = band_len;
+    p.band_off = band_off; p.band_w = band_w; p.nnz = nnz; p.hop = hop; p.n_mels = n_mels;
+    p.M = (int)(1 + (n_samples - n_fft) / hop); p.eps = eps; p.mean = mean; p.stdv = stdv; p.out = out;
+    const size_t smem = logmel_fused_smem(hop);
+    static bool attr_set = false;
+    if (!attr_set) {
+        API_TRY(cudaFuncSetAttribute(k_logmel_fft1024, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    const long long grid = (long long)B * ((p.M + CRK_MEL_FPC - 1) / CRK_MEL_FPC);
+    TimedLaunch tl(CRK_K_LOGMEL, (cudaStream_t)stream, 0.0);
+    k_logmel_fft1024<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(p);
     API_TRY(launch_check());
     return CRK_OK;
 }

@@ -34,7 +34,7 @@ namespace crk {
 // Every kernel launch of the library bumps the counter (bench.py reports it as gpu_launches).
 // crk_timing_enable(id) makes the launch helpers of kernel family `id` record a cudaEvent pair
 // on the launch stream around each launch; crk_timing_read() synchronises and sums them.
-enum { CRK_K_RESBLOCK_FWD = 1, CRK_K_WGRAD = 2, CRK_K_CONV = 3, CRK_K_BWD_GATE = 4, CRK_K_VQ_ARGMIN = 5, CRK_K_MAX = 8 };
+enum { CRK_K_RESBLOCK_FWD = 1, CRK_K_WGRAD = 2, CRK_K_CONV = 3, CRK_K_BWD_GATE = 4, CRK_K_VQ_ARGMIN = 5, CRK_K_LOGMEL = 6, CRK_K_MAX = 8 };
 struct Instr {
     unsigned long long launches = 0;
     int enabled_id = 0;

@@ -365,14 +365,55 @@ def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, step_dev):
            C.c_float(beta1), C.c_float(beta2), C.c_float(eps), L.ptr(step_dev))
 
 
-def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None):
-    """wav (B, n_samples) -> (B, n_frames, n_mels);  frames start at m*hop (no centring here)."""
+_MEL_BANDS = {}
+MEL_FUSED_MAXNNZ = 2048
+
+
+def _mel_bands(mel_basis):
+    """Non-zero runs of a (bins, n_mels) mel basis: (band_start, band_len, band_off, band_w, nnz) on its device,
+    or None when the basis is not banded enough for the fused kernel.  Cached per basis version (one host sync)."""
+    key = (mel_basis.data_ptr(), mel_basis._version, tuple(mel_basis.shape), str(mel_basis.device))
+    hit = _MEL_BANDS.get(key)
+    if hit is not None:
+        return hit[0]
+    w = mel_basis.detach().float().cpu().numpy()
+    start, length, off, vals = [], [], [], []
+    for m in range(w.shape[1]):
+        nz = w[:, m].nonzero()[0]
+        lo, hi = (int(nz[0]), int(nz[-1]) + 1) if len(nz) else (0, 0)
+        start.append(lo), length.append(hi - lo), off.append(len(vals))
+        vals.extend(w[lo:hi, m].tolist())
+    bands = None
+    if 0 < len(vals) <= MEL_FUSED_MAXNNZ:
+        dev = mel_basis.device
+        it = lambda a: torch.tensor(a, dtype=torch.int32, device=dev)
+        bands = (it(start), it(length), it(off), torch.tensor(vals, dtype=_f32, device=dev), len(vals))
+    if len(_MEL_BANDS) > 16:
+        _MEL_BANDS.clear()
+    _MEL_BANDS[key] = (bands, mel_basis)  # keeps the basis alive so the data_ptr key cannot be recycled
+    return bands
+
+
+def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None, fused=None):
+    """wav (B, n_samples) -> (B, n_frames, n_mels);  frames start at m*hop (no centring here).
+
+    n_fft = 1024 with a banded basis (every recipe) runs the one-kernel front end `crk_logmel_fused_fwd`;
+    anything else (or fused=False) the cuFFT path `crk_logmel_fwd`."""
     L.require_cuda(wav, window, mel_basis)
     wav = wav.float().contiguous()
     B, n = wav.shape
     n_mels = mel_basis.shape[1]
     M = 1 + (n - n_fft) // hop
     out = torch.empty(B, M, n_mels, dtype=_f32, device=wav.device)
+    can_fuse = n_fft == 1024 and hop <= 512 and n_mels <= 128 and mel_basis.shape[0] == 513
+    bands = _mel_bands(mel_basis) if (can_fuse and fused is not False) else None
+    if fused and bands is None:
+        raise ValueError("the fused log-mel kernel needs n_fft = 1024, hop <= 512, n_mels <= 128 and a banded basis")
+    if bands is not None:
+        st, ln, of, bw, nnz = bands
+        L.call("crk_logmel_fused_fwd", L.ptr(wav), B, n, L.ptr(window), L.ptr(st), L.ptr(ln), L.ptr(of), L.ptr(bw),
+               nnz, n_fft, hop, n_mels, C.c_float(eps), L.ptr(mean), L.ptr(std), L.ptr(out))
+        return out
     ws = _empty(L.lib().crk_logmel_ws_floats(B, M, n_fft), wav.device)
     L.call("crk_logmel_fwd", L.ptr(wav), B, n, L.ptr(window), L.ptr(mel_basis), n_fft, hop,
            n_mels, C.c_float(eps), L.ptr(mean), L.ptr(std), L.ptr(out), L.ptr(ws))

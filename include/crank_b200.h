@@ -257,6 +257,14 @@ long long crk_logmel_ws_floats(int B, int n_frames, int n_fft);
 int crk_logmel_fwd(const float* wav, int B, long long n_samples, const float* window,
                    const float* mel_basis, int n_fft, int hop, int n_mels, float eps,
                    const float* mean, const float* stdv, float* out, float* ws, void* stream);
+/* fused front end, one kernel and one pass over the waveform (n_fft = 1024; else CRK_ERR_UNSUPPORTED -> use
+ * crk_logmel_fwd): framing + window + radix-4 FFT (two real frames per complex transform) + |.| + BANDED mel projection +
+ * clamp / log10 / optional scaler.  Replaces the same reference code as crk_logmel_fwd (crank/net/module/mlfb.py:134-171,
+ * crank/feature/feature.py:126-145).  The mel basis is passed by its non-zero runs: mel channel m sums bins
+ * [band_start[m], band_start[m] + band_len[m]) with weights band_w[band_off[m] ...] (nnz <= 2048 in total). */
+int crk_logmel_fused_fwd(const float* wav, int B, long long n_samples, const float* window, const int* band_start,
+                         const int* band_len, const int* band_off, const float* band_w, int nnz, int n_fft, int hop,
+                         int n_mels, float eps, const float* mean, const float* stdv, float* out, void* stream);
 
 #ifdef __cplusplus
 }

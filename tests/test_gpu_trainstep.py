@@ -117,7 +117,7 @@ def test_generator_forward_matches_oracle_and_golden():
 
 
 @pytest.mark.parametrize("kind", ["vqvae", "lsgan", "cyclegan", "stargan"])
-def test_train_steps_match_oracle_and_golden(kind):
+def test_train_steps_match_oracle_and_golden(kind, rms_tol=3e-2):
     from crank_b200.synthetic import clone_batch, make_batch, to_device
 
     gold = np.load(GOLD)
@@ -165,7 +165,7 @@ def test_train_steps_match_oracle_and_golden(kind):
             rms = ((mp - mo).pow(2).mean().sqrt() / mo.pow(2).mean().sqrt()).item()
             frac = ((mp - mo).abs() > 2e-2 * mo.abs().max()).double().mean().item()
             worst_rms, worst_frac = max(worst_rms, rms), max(worst_frac, frac)
-            assert rms <= 3e-2, f"{kind}: parameter {k}.{name}: RMS movement error {rms:.2e}"
+            assert rms <= rms_tol, f"{kind}: parameter {k}.{name}: RMS movement error {rms:.2e}"
     print(f"{kind}: parameter movement after 2 steps: worst RMS err {worst_rms:.2e}, worst outlier fraction {worst_frac:.2e}")
 
 def test_weight_cache_is_invalidated_by_fused_adam():
