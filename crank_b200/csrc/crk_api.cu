@@ -605,4 +605,45 @@ int crk_logmel_fused_fwd(const float* wav, int B, long long n_samples, const flo
     return CRK_OK;
 }
 
+// backward of crk_logmel_fused_fwd w.r.t. the window and / or the waveform (learnable STFT windows, mlfb.py:72-90).
+// `bin_*`: the transposed band table (per FFT bin 0..512 the run of mel channels whose filter covers it).
+// dwin (1024 floats) and / or dwav (B x n_samples, accumulated into: the caller zero-initialises it) may be NULL;
+// ws: crk_logmel_bwd_ws_floats(B, n_samples, hop) floats (per-CTA partial rows of d window).
+long long crk_logmel_bwd_ws_floats(int B, long long n_samples, int hop) {
+    if (B < 1 || hop < 1 || n_samples < 1024) return 0;
+    const long long M = 1 + (n_samples - 1024) / hop;
+    return (long long)B * ((M + CRK_MEL_FPC - 1) / CRK_MEL_FPC) * 1024;
+}
+int crk_logmel_fused_bwd(const float* wav, int B, long long n_samples, const float* window, const int* band_start,
+                         const int* band_len, const int* band_off, const float* band_w, int nnz, const int* bin_start,
+                         const int* bin_len, const int* bin_off, const float* bin_w, int n_fft, int hop, int n_mels,
+                         float eps, const float* mean, const float* stdv, const float* dout, float* dwin, float* dwav,
+                         float* ws, void* stream) {
+    if (!wav || !window || !band_start || !band_len || !band_off || !band_w || !bin_start || !bin_len || !bin_off || !bin_w ||
+        !dout || B < 1 || hop < 1 || (dwin && !ws))
+        return CRK_ERR_ARG;
+    if (n_fft != 1024 || n_mels < 1 || n_mels > 128 || nnz < 1 || nnz > CRK_MEL_MAXNNZ || hop > 512) return CRK_ERR_UNSUPPORTED;
+    if (n_samples < n_fft) return CRK_ERR_ARG;
+    LogmelBwdParams q;
+    LogmelParams& p = q.f;
+    p.wav = wav; p.n_samples = n_samples; p.window = window; p.band_start = band_start; p.band_len = band_len;
+    p.band_off = band_off; p.band_w = band_w; p.nnz = nnz; p.hop = hop; p.n_mels = n_mels;
+    p.M = (int)(1 + (n_samples - n_fft) / hop); p.eps = eps; p.mean = mean; p.stdv = stdv; p.out = nullptr;
+    q.dout = dout; q.bin_start = bin_start; q.bin_len = bin_len; q.bin_off = bin_off; q.bin_w = bin_w;
+    q.dwin_part = dwin ? ws : nullptr; q.dwav = dwav;
+    static bool attr_set = false;
+    if (!attr_set) {
+        API_TRY(cudaFuncSetAttribute(k_logmel_bwd_fft1024, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        attr_set = true;
+    }
+    const long long grid = (long long)B * ((p.M + CRK_MEL_FPC - 1) / CRK_MEL_FPC);
+    k_logmel_bwd_fft1024<<<(unsigned)grid, 256, logmel_bwd_smem(hop), (cudaStream_t)stream>>>(q);
+    API_TRY(launch_check());
+    if (dwin) {
+        k_logmel_dwin_reduce<<<4, 256, 0, (cudaStream_t)stream>>>(ws, (int)grid, dwin);
+        API_TRY(launch_check());
+    }
+    return CRK_OK;
+}
+
 }  // extern "C"

@@ -100,6 +100,9 @@ SIGNATURES = {
     "crk_logmel_ws_floats": (i64, [i32, i32, i32]),
     "crk_logmel_fwd": (i32, [vp, i32, i64, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
     "crk_logmel_fused_fwd": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp]),
+    "crk_logmel_bwd_ws_floats": (i64, [i32, i64, i32]),
+    "crk_logmel_fused_bwd": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp,
+                                   vp, vp, vp, vp]),
 }
 
 PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2}

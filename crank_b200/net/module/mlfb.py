@@ -3,8 +3,8 @@
 API mirror of crank/net/module/mlfb.py:19-171 (LogMelFilterBankLayer and its three sub-layers).
 The mel basis is the Slaney-scale / Slaney-norm filterbank `librosa.filters.mel` would build
 (mlfb.py:27-33); librosa is not a dependency here, the basis is computed in `mel_basis()` below.
-Only the fixed "hann" window is supported on the kernel path (the learnable "param"/"conv" windows
-of mlfb.py:72-90 are SURVEY.md section 8f rank 4, not built yet).
+n_fft = 1024 (every recipe) runs ONE fused kernel (crk_logmel_fused_fwd: framing + window + FFT + banded mel + log10 +
+scaler); the learnable "param" / "conv" windows of mlfb.py:72-90 get their gradients from crk_logmel_fused_bwd.
 """
 
 import numpy as np
@@ -54,22 +54,47 @@ class MLFBLayer(nn.Module):
 
 
 class STFTLayer(nn.Module):
+    """Holds the STFT geometry and window of crank/net/module/mlfb.py:45-110; the transform itself runs inside the
+    fused log-mel kernel (LogMelFilterBankLayer.forward).  Window types (mlfb.py:64-90):
+      "hann"   fixed periodic hann;
+      "param"  the window is a learnable parameter `window` (initialised to scipy get_window("hann") = periodic hann);
+               its gradient comes from crk_logmel_fused_bwd;
+      "conv"   a learnable pre-filter `window_conv` = Conv1d(1, 24, 65, padding 32) + Sigmoid, averaged over its 24
+               channels, replaces the waveform and the STFT uses a rectangular window; the 24-channel pre-filter is a
+               stock torch conv (cuDNN, off the default path: `raw_window_type: hann` in every recipe), the gradient
+               reaches it through the d wav output of crk_logmel_fused_bwd."""
+
     def __init__(self, fs=22050, hop_size=256, fft_size=1024, win_length=None, window="hann",
                  center=True, pad_mode="reflect", return_complex=False):
         super().__init__()
-        if window != "hann":
-            raise NotImplementedError("only the fixed hann window runs on the kernel path")
+        if window not in ("hann", "param", "conv"):
+            raise NotImplementedError(f"window {window!r}: hann / param / conv are built")
         self.hop_size = hop_size
         self.fft_size = fft_size
         self.win_length = fft_size if win_length is None else win_length
         self.center = center
         self.pad_mode = pad_mode
         self.window_type = window
-        win = torch.hann_window(self.win_length)
+        if window == "param":
+            if self.win_length != fft_size:
+                raise NotImplementedError("the learnable window spans the whole FFT frame (win_length == fft_size)")
+            self.register_parameter("window", nn.Parameter(torch.hann_window(self.win_length), requires_grad=True))
+        elif window == "conv":
+            kernel_size = 65
+            self.window_conv = nn.Sequential(
+                nn.Conv1d(in_channels=1, out_channels=24, kernel_size=kernel_size, stride=1,
+                          padding=(kernel_size - 1) // 2),
+                nn.Sigmoid(),
+            )
+        win = torch.hann_window(self.win_length) if window != "conv" else torch.ones(self.win_length)
         if self.win_length < fft_size:
             lpad = (fft_size - self.win_length) // 2
             win = torch.nn.functional.pad(win, (lpad, fft_size - self.win_length - lpad))
         self.register_buffer("window_padded", win, persistent=False)
+
+    @property
+    def learnable(self):
+        return self.window_type in ("param", "conv")
 
 
 class MLFBScalerLayer(nn.Module):
@@ -93,16 +118,25 @@ class LogMelFilterBankLayer(nn.Module):
         self.mlfb_layer = MLFBLayer(fs, fft_size, n_mels, fmin, fmax)
         self.scaler_layer = MLFBScalerLayer(scaler) if scaler is not None else None
 
-    @torch.no_grad()
     def forward(self, x):
         """x (B, n_samples) raw waveform -> (B, n_frames, n_mels) log10 mel (optionally standardised)."""
         st = self.stft_layer
         x = x.float()
-        if st.center:
-            x = torch.nn.functional.pad(x.unsqueeze(1), (st.fft_size // 2, st.fft_size // 2),
-                                        mode=st.pad_mode).squeeze(1)
         mean = std = None
         if self.scaler_layer is not None:
             mean, std = self.scaler_layer.mean.data, self.scaler_layer.std.data
-        return ops.logmel(x, st.window_padded, self.mlfb_layer.mel_basis, st.fft_size, st.hop_size,
-                          eps=self.mlfb_layer.eps, mean=mean, std=std)
+        if st.learnable:
+            if st.window_type == "conv":      # mlfb.py:93-96
+                x = st.window_conv(x.unsqueeze(1)).mean(dim=1)
+            if st.center:
+                x = torch.nn.functional.pad(x.unsqueeze(1), (st.fft_size // 2, st.fft_size // 2),
+                                            mode=st.pad_mode).squeeze(1)
+            window = st.window if st.window_type == "param" else st.window_padded
+            return ops.logmel_learnable(x, window, self.mlfb_layer.mel_basis, st.fft_size, st.hop_size,
+                                        eps=self.mlfb_layer.eps, mean=mean, std=std)
+        with torch.no_grad():
+            if st.center:
+                x = torch.nn.functional.pad(x.unsqueeze(1), (st.fft_size // 2, st.fft_size // 2),
+                                            mode=st.pad_mode).squeeze(1)
+            return ops.logmel(x, st.window_padded, self.mlfb_layer.mel_basis, st.fft_size, st.hop_size,
+                              eps=self.mlfb_layer.eps, mean=mean, std=std)

@@ -1,9 +1,8 @@
 """Trainer base: step loop, schedulers, checkpointing, conditioning vectors, loss bookkeeping.
 
 API mirror of crank/net/trainer/basetrainer.py:26-309 (TrainerWrapper, BaseTrainer).  What is NOT
-rebuilt: the CPU wav / HDF5 dumping of dev/eval/reconstruction (basetrainer.py:322-435 --
-Griffin-Lim / WORLD synthesis through joblib, out of scope per SURVEY.md section 2 #7); `_generate_cvwav`
-is a hook that subclasses / callers may override.
+rebuilt: the HDF5 dumping and WORLD synthesis of dev/eval/reconstruction (basetrainer.py:322-435, out of scope per
+SURVEY.md section 2 #7).  Griffin-Lim synthesis of mlfb outputs (`_generate_cvwav`) runs on the device.
 
 Differences by design: every loss scalar of a step is fetched with ONE packed device->host copy
 (`_parse_loss`), replacing the reference's ~15 `.item()` syncs (basetrainer.py:208-231).
@@ -265,9 +264,62 @@ class BaseTrainer(object):
             out.append((conv - float(glob.mean_[0])) / float(glob.scale_[0]))
         return torch.stack(out, dim=0).float()
 
-    def _generate_cvwav(self, batch, outputs, cv_spkr_name=None, **kwargs):
-        """Out of scope (CPU Griffin-Lim / WORLD / HDF5 dumping, basetrainer.py:322-435)."""
-        return None
+    def _generate_cvwav(self, batch, outputs, cv_spkr_name=None, tdir="dev_wav", save_hdf5=True, save_decoded=True,
+                        n_samples=1):
+        """Decoded features -> waveforms (basetrainer.py:322-420), mlfb outputs only: the inverse scaler and Griffin-Lim
+        run on the DEVICE (crank_b200.utils.griffin_lim; the reference hands each utterance to a joblib CPU worker
+        running librosa, basetrainer.py:400-418), utterances of equal length are iterated as one batch, 16-bit WAVs are
+        written with the stdlib `wave` module.  Not rebuilt (out of scope): HDF5 dumps
+        (`save_hdf5`, needs h5py) and WORLD synthesis of mcep outputs -- both are skipped with a log line.
+        Returns {wav path: float32 waveform tensor on the device} (the reference returns nothing)."""
+        if not save_decoded:
+            return {}
+        if self.conf["output_feat_type"] != "mlfb":
+            logging.info("crank_b200: WORLD synthesis of mcep outputs is not rebuilt; skipping %s", tdir)
+            return {}
+        import wave
+
+        import numpy as np
+
+        from ...utils import mlfb2wav
+
+        tdir = self.expdir / tdir / str(self.steps)
+        fc = self.feat_conf
+        dec = outputs["decoded"]
+        names = []
+        for n in range(dec.size(0)):
+            org = batch["org_spkr_name"][n]
+            cv = org if cv_spkr_name is None else cv_spkr_name
+            names.append(tdir / f"{batch['flbl'][n]}_org-{org}_cv-{cv}.wav")
+        picked = list(range(dec.size(0)))
+        if not (n_samples == -1 or n_samples > len(picked)):
+            picked = random.sample(picked, n_samples)
+        sc = None
+        if self.scaler is not None and "mlfb" in self.scaler and "mlfb" not in self.conf.get("ignore_scaler", []):
+            ms = self.scaler["mlfb"]
+            sc = (torch.as_tensor(np.asarray(ms.mean_), dtype=torch.float32, device=dec.device),
+                  torch.as_tensor(np.asarray(ms.scale_), dtype=torch.float32, device=dec.device))
+        by_len = {}
+        for n in picked:
+            by_len.setdefault(int(batch["flen"][n]), []).append(n)
+        wavs = {}
+        for flen, ids in by_len.items():
+            feats = torch.stack([dec[n, :flen] for n in ids]).float()
+            if sc is not None:
+                feats = feats * sc[1] + sc[0]                       # StandardScaler.inverse_transform
+            y = mlfb2wav(feats, fs=fc["fs"], n_mels=fc["mlfb_dim"], fftl=fc["fftl"], win_length=fc["win_length"],
+                         hop_size=fc["hop_size"], fmin=fc["fmin"], fmax=fc["fmax"])
+            for j, n in enumerate(ids):
+                wavs[names[n]] = y[j]
+        for path, y in wavs.items():
+            Path(path).parent.mkdir(parents=True, exist_ok=True)
+            pcm = (y.clamp(-1.0, 1.0) * 32767.0).round().to(torch.int16).cpu().numpy()
+            with wave.open(str(path), "wb") as f:
+                f.setnchannels(1)
+                f.setsampwidth(2)
+                f.setframerate(int(fc["fs"]))
+                f.writeframes(pcm.tobytes())
+        return wavs
 
 
 import contextlib

@@ -369,29 +369,81 @@ _MEL_BANDS = {}
 MEL_FUSED_MAXNNZ = 2048
 
 
-def _mel_bands(mel_basis):
-    """Non-zero runs of a (bins, n_mels) mel basis: (band_start, band_len, band_off, band_w, nnz) on its device,
-    or None when the basis is not banded enough for the fused kernel.  Cached per basis version (one host sync)."""
-    key = (mel_basis.data_ptr(), mel_basis._version, tuple(mel_basis.shape), str(mel_basis.device))
-    hit = _MEL_BANDS.get(key)
-    if hit is not None:
-        return hit[0]
-    w = mel_basis.detach().float().cpu().numpy()
+def _runs(w):
+    """per column of w: first/last non-zero row as (start, len, off, vals)"""
     start, length, off, vals = [], [], [], []
     for m in range(w.shape[1]):
         nz = w[:, m].nonzero()[0]
         lo, hi = (int(nz[0]), int(nz[-1]) + 1) if len(nz) else (0, 0)
         start.append(lo), length.append(hi - lo), off.append(len(vals))
         vals.extend(w[lo:hi, m].tolist())
+    return start, length, off, vals
+
+
+def _mel_bands(mel_basis):
+    """Non-zero runs of a (bins, n_mels) mel basis, per mel channel (band_start, band_len, band_off, band_w, nnz) and
+    transposed, per bin (bin_start, bin_len, bin_off, bin_w), on its device; None when the basis is not banded enough
+    for the fused kernels.  Cached per basis version (one host sync)."""
+    key = (mel_basis.data_ptr(), mel_basis._version, tuple(mel_basis.shape), str(mel_basis.device))
+    hit = _MEL_BANDS.get(key)
+    if hit is not None:
+        return hit[0]
+    w = mel_basis.detach().float().cpu().numpy()
+    start, length, off, vals = _runs(w)
+    tstart, tlength, toff, tvals = _runs(w.T.copy())
     bands = None
     if 0 < len(vals) <= MEL_FUSED_MAXNNZ:
         dev = mel_basis.device
-        it = lambda a: torch.tensor(a, dtype=torch.int32, device=dev)
-        bands = (it(start), it(length), it(off), torch.tensor(vals, dtype=_f32, device=dev), len(vals))
+        it = lambda a: torch.tensor(a, dtype=torch.int32, device=dev)      # noqa: E731
+        ft = lambda a: torch.tensor(a, dtype=_f32, device=dev)             # noqa: E731
+        bands = (it(start), it(length), it(off), ft(vals), len(vals), it(tstart), it(tlength), it(toff), ft(tvals))
     if len(_MEL_BANDS) > 16:
         _MEL_BANDS.clear()
     _MEL_BANDS[key] = (bands, mel_basis)  # keeps the basis alive so the data_ptr key cannot be recycled
     return bands
+
+
+class LogMelFn(torch.autograd.Function):
+    """Fused front end with a backward to the STFT window and / or the waveform (crk_logmel_fused_{fwd,bwd}): the
+    learnable "param" / "conv" windows of crank/net/module/mlfb.py:72-90."""
+
+    @staticmethod
+    def forward(ctx, wav, window, mel_basis, n_fft, hop, eps, mean, std):
+        L.require_cuda(wav, window, mel_basis)
+        wav = wav.float().contiguous()
+        window = window.float().contiguous()
+        bands = _mel_bands(mel_basis) if (n_fft == 1024 and hop <= 512 and mel_basis.shape[1] <= 128 and
+                                          mel_basis.shape[0] == 513) else None
+        if bands is None:
+            raise ValueError("learnable STFT windows need the fused log-mel kernel: n_fft = 1024, hop <= 512, a banded basis")
+        B, n = wav.shape
+        M = 1 + (n - n_fft) // hop
+        out = torch.empty(B, M, mel_basis.shape[1], dtype=_f32, device=wav.device)
+        st, ln, of, bw, nnz = bands[:5]
+        L.call("crk_logmel_fused_fwd", L.ptr(wav), B, n, L.ptr(window), L.ptr(st), L.ptr(ln), L.ptr(of), L.ptr(bw),
+               nnz, n_fft, hop, out.shape[2], C.c_float(eps), L.ptr(mean), L.ptr(std), L.ptr(out))
+        ctx.save_for_backward(wav, window)
+        ctx.misc = (bands, n_fft, hop, eps, mean, std)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        wav, window = ctx.saved_tensors
+        bands, n_fft, hop, eps, mean, std = ctx.misc
+        st, ln, of, bw, nnz, tst, tln, tof, tbw = bands
+        B, n = wav.shape
+        dout = dout.float().contiguous()
+        dwav = torch.zeros_like(wav) if ctx.needs_input_grad[0] else None
+        dwin = torch.empty_like(window) if ctx.needs_input_grad[1] else None
+        ws = _empty(L.lib().crk_logmel_bwd_ws_floats(B, n, hop), wav.device) if dwin is not None else None
+        L.call("crk_logmel_fused_bwd", L.ptr(wav), B, n, L.ptr(window), L.ptr(st), L.ptr(ln), L.ptr(of), L.ptr(bw), nnz,
+               L.ptr(tst), L.ptr(tln), L.ptr(tof), L.ptr(tbw), n_fft, hop, dout.shape[2], C.c_float(eps), L.ptr(mean),
+               L.ptr(std), L.ptr(dout), L.ptr(dwin), L.ptr(dwav), L.ptr(ws))
+        return dwav, dwin, None, None, None, None, None, None
+
+
+def logmel_learnable(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None):
+    return LogMelFn.apply(wav, window, mel_basis, n_fft, hop, eps, mean, std)
 
 
 def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None, fused=None):
@@ -410,7 +462,7 @@ def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None, f
     if fused and bands is None:
         raise ValueError("the fused log-mel kernel needs n_fft = 1024, hop <= 512, n_mels <= 128 and a banded basis")
     if bands is not None:
-        st, ln, of, bw, nnz = bands
+        st, ln, of, bw, nnz = bands[:5]
         L.call("crk_logmel_fused_fwd", L.ptr(wav), B, n, L.ptr(window), L.ptr(st), L.ptr(ln), L.ptr(of), L.ptr(bw),
                nnz, n_fft, hop, n_mels, C.c_float(eps), L.ptr(mean), L.ptr(std), L.ptr(out))
         return out

@@ -265,6 +265,18 @@ int crk_logmel_fwd(const float* wav, int B, long long n_samples, const float* wi
 int crk_logmel_fused_fwd(const float* wav, int B, long long n_samples, const float* window, const int* band_start,
                          const int* band_len, const int* band_off, const float* band_w, int nnz, int n_fft, int hop,
                          int n_mels, float eps, const float* mean, const float* stdv, float* out, void* stream);
+/* backward of crk_logmel_fused_fwd w.r.t. the STFT window (dwin: 1024 floats, overwritten) and / or the waveform
+ * (dwav: B x n_samples, ACCUMULATED into -- zero it first); either may be NULL.  Serves the learnable windows of
+ * crank/net/module/mlfb.py:72-90 ("param": the window is an nn.Parameter; "conv": a learnable pre-filter feeds the
+ * STFT, so the gradient must reach the waveform), whose backward the reference gets from autograd through torch.stft.
+ * bin_*: transposed band table (per FFT bin 0..512 the run [bin_start, bin_start + bin_len) of mel channels whose
+ * filter covers the bin, weights bin_w[bin_off ...]).  ws: crk_logmel_bwd_ws_floats() floats. */
+long long crk_logmel_bwd_ws_floats(int B, long long n_samples, int hop);
+int crk_logmel_fused_bwd(const float* wav, int B, long long n_samples, const float* window, const int* band_start,
+                         const int* band_len, const int* band_off, const float* band_w, int nnz, const int* bin_start,
+                         const int* bin_len, const int* bin_off, const float* bin_w, int n_fft, int hop, int n_mels,
+                         float eps, const float* mean, const float* stdv, const float* dout, float* dwin, float* dwav,
+                         float* ws, void* stream);
 
 #ifdef __cplusplus
 }

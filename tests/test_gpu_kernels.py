@@ -485,3 +485,84 @@ def test_fused_logmel_matches_cufft_path_and_oracle(hop, n_frames, B):
         e_p = np.abs(plain.cpu().numpy() - ref).max() / np.abs(ref).max()
         print(f"fused log-mel hop {hop} M {n_frames}: rel-to-max vs float64 oracle {e_f:.2e} (cuFFT path {e_p:.2e})")
         assert e_f <= 1e-4, e_f
+
+
+def _torch_logmel_ref(x, win, basis, hop, mean=None, std=None, eps=1e-10):
+    """float64 autograd restatement of mlfb.py:134-171 with center=False: frames * window -> rfft -> |.| -> mel -> log10"""
+    fr = x.unfold(-1, 1024, hop) * win
+    mag = torch.fft.rfft(fr, dim=-1).abs()
+    out = torch.clamp(mag @ basis, min=eps).log10()
+    if mean is not None:
+        out = (out - mean) / std
+    return out
+
+
+@pytest.mark.parametrize("hop,n_frames,B,scaler", [(128, 37, 2, True), (128, 16, 1, False), (240, 5, 2, False)])
+def test_fused_logmel_backward_matches_float64_autograd(hop, n_frames, B, scaler):
+    """crk_logmel_fused_bwd: d loss / d window and d loss / d wav of the fused front end against torch float64 autograd
+    through the same computation (what the reference's learnable windows get from autograd, mlfb.py:72-110)."""
+    from crank_b200 import ops
+    from crank_b200.net.module.mlfb import mel_basis
+
+    g = torch.Generator().manual_seed(7 * hop + n_frames)
+    n = 1024 + (n_frames - 1) * hop + 3
+    t = torch.arange(n)[None] / 24000.0
+    wav = 0.3 * torch.sin(2 * np.pi * 310.0 * t * (1 + torch.arange(B)[:, None])) + 0.05 * torch.randn(B, n, generator=g)
+    basis = torch.from_numpy(mel_basis(24000, 1024, 80, 80, 7600).T.copy())
+    win = torch.hann_window(1024) * (1.0 + 0.1 * torch.randn(1024, generator=g))
+    mean = torch.randn(80, generator=g) if scaler else None
+    std = (0.5 + torch.rand(80, generator=g)) if scaler else None
+    R = torch.randn(B, n_frames, 80, generator=g)
+    xr = wav.double().requires_grad_(True)
+    wr = win.double().requires_grad_(True)
+    ref = _torch_logmel_ref(xr, wr, basis.double(), hop, None if mean is None else mean.double(),
+                            None if std is None else std.double())
+    (ref * R.double()).sum().backward()
+    xp = wav.to(_dev()).requires_grad_(True)
+    wp = win.to(_dev()).requires_grad_(True)
+    out = ops.logmel_learnable(xp, wp, basis.to(_dev()), 1024, hop, mean=None if mean is None else mean.to(_dev()),
+                               std=None if std is None else std.to(_dev()))
+    (out * R.to(_dev())).sum().backward()
+    e_o = (out.detach().cpu().double() - ref.detach()).abs().max() / ref.detach().abs().max()
+    e_w = (wp.grad.cpu().double() - wr.grad).abs().max() / wr.grad.abs().max()
+    e_x = (xp.grad.cpu().double() - xr.grad).abs().max() / xr.grad.abs().max()
+    print(f"fused log-mel backward hop {hop} M {n_frames}: out {e_o:.2e}  d window {e_w:.2e}  d wav {e_x:.2e}")
+    assert e_o <= 1e-4 and e_w <= 1e-4 and e_x <= 1e-4, (e_o, e_w, e_x)
+
+
+@pytest.mark.parametrize("window", ["param", "conv"])
+def test_learnable_stft_windows_train(window):
+    """LogMelFilterBankLayer(window="param" / "conv") (mlfb.py:72-96): forward and the gradients of the learnable parameters
+    against a float64 torch restatement with the same parameters."""
+    from crank_b200.net.module.mlfb import LogMelFilterBankLayer
+
+    torch.manual_seed(3)
+    layer = LogMelFilterBankLayer(fs=24000, hop_size=128, fft_size=1024, win_length=1024, window=window, center=False,
+                                  n_mels=80, fmin=80, fmax=7600).to(_dev())
+    g = torch.Generator().manual_seed(11)
+    n = 1024 + 20 * 128
+    wav = 0.2 * torch.randn(2, n, generator=g)
+    R = torch.randn(2, 21, 80, generator=g)
+    out = layer(wav.to(_dev()))
+    (out * R.to(_dev())).sum().backward()
+    basis = layer.mlfb_layer.mel_basis.detach().cpu().double()
+    if window == "param":
+        w = layer.stft_layer.window.detach().cpu().double().requires_grad_(True)
+        ref = _torch_logmel_ref(wav.double(), w, basis, 128)
+        (ref * R.double()).sum().backward()
+        pairs = [(layer.stft_layer.window.grad, w.grad)]
+    else:
+        conv = torch.nn.Conv1d(1, 24, 65, padding=32).double()
+        conv.load_state_dict({k: v.detach().cpu().double() for k, v in layer.stft_layer.window_conv[0].state_dict().items()})
+        xr = torch.sigmoid(conv(wav.double().unsqueeze(1))).mean(dim=1)
+        ref = _torch_logmel_ref(xr, torch.ones(1024, dtype=torch.float64), basis, 128)
+        (ref * R.double()).sum().backward()
+        pairs = [(layer.stft_layer.window_conv[0].weight.grad, conv.weight.grad),
+                 (layer.stft_layer.window_conv[0].bias.grad, conv.bias.grad)]
+    e_o = (out.detach().cpu().double() - ref.detach()).abs().max() / ref.detach().abs().max()
+    assert e_o <= 1e-4, e_o
+    for got, want in pairs:
+        assert got is not None
+        e = (got.cpu().double() - want).abs().max() / want.abs().max()
+        print(f"learnable window {window}: forward {e_o:.2e}, parameter gradient rel err {e:.2e}")
+        assert e <= 2e-4, e
