@@ -16,6 +16,7 @@
 #include "crk_tc_probe.cuh"
 #include "crk_vq.cuh"
 #include "crk_vq_tc.cuh"
+#include "crk_vq_fast.cuh"
 
 namespace crk {
 static thread_local char g_cuda_err[256] = "";
@@ -299,6 +300,61 @@ int crk_vq_ema(const float* counts, const float* esum, float* ema_size, float* e
     k_vq_ema_size<<<1, 512, 0, (cudaStream_t)stream>>>(counts, ema_size, decay, one_m_decay, eps, keps, K);
     API_TRY(launch_check());
     k_vq_ema_w<<<cdiv(K * D, 256), 256, 0, (cudaStream_t)stream>>>(esum, ema_size, ema_w, W, decay, one_m_decay, K, D);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+// ---- round 2: single-pass TF32 argmin with a resident codebook, fused EMA (crk_vq_fast.cuh) ----
+long long crk_vq_op_floats(int K, int D) {
+    if (D != 64 || K < 128 || (K % 128) != 0 || K > 512) return -1;
+    return vq_op_floats(K);
+}
+int crk_vq_pack_op(const float* W, float* opblob, int K, int D, void* stream) {
+    if (!W || !opblob) return CRK_ERR_ARG;
+    if (D != 64 || K < 128 || (K % 128) != 0 || K > 512) return CRK_ERR_UNSUPPORTED;
+    k_vq_pack_op<<<cdiv(K, 128), 128, 0, (cudaStream_t)stream>>>(W, opblob, K);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+int crk_vq_argmin_fast(const float* x, int ldx, const float* opblob, long long* idx, float* e, int lde, float* qx,
+                       int ldqx, long long F, int K, int D, void* stream) {
+    if (!x || !opblob || !idx || !e || !qx || F < 1) return CRK_ERR_ARG;
+    if (D != 64 || K < 128 || (K % 128) != 0 || K > 512) return CRK_ERR_UNSUPPORTED;
+    VqFastParams q;
+    q.p.x = x; q.p.ldx = ldx; q.p.W = nullptr; q.p.WT = nullptr; q.p.wn = nullptr; q.p.idx = idx; q.p.e = e; q.p.lde = lde;
+    q.p.qx = qx; q.p.ldqx = ldqx; q.p.F = F; q.p.K = K;
+    q.opblob = opblob;
+    static bool attr_set = false;
+    if (!attr_set) {
+        API_TRY(cudaFuncSetAttribute(k_vq_argmin_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        attr_set = true;
+    }
+    const long long tiles = cdivl(F, 128);
+    const int sms = device_sm_count();
+    TimedLaunch tl(CRK_K_VQ_ARGMIN, (cudaStream_t)stream, 2.0 * F * 64.0 * K);
+    k_vq_argmin_tf32<<<(unsigned)(tiles < sms ? tiles : sms), 256, vq_fast_smem(K), (cudaStream_t)stream>>>(q);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+// statistics of one quantiser call into `stats` = [counts K | esum D*K | ticket (1 int, zeroed here)]
+long long crk_vq_stats_floats(int K, int D) { return (K < 1 || D < 1) ? -1 : (long long)K + (long long)K * D + 4; }
+int crk_vq_stats_fused(const float* x, int ldx, const long long* idx, float* stats, float* ws, long long F, int K, int D,
+                       void* stream) {
+    if (!stats) return CRK_ERR_ARG;
+    int rc = crk_vq_stats(x, ldx, idx, stats, stats + K, ws, F, K, D, stream);
+    if (rc != CRK_OK) return rc;
+    API_TRY(cudaMemsetAsync(stats + (size_t)K + (size_t)K * D, 0, 4 * sizeof(float), (cudaStream_t)stream));
+    return CRK_OK;
+}
+int crk_vq_ema_fused(float* stats, float* ema_size, float* ema_w, float* W, float* opblob, float decay, float eps, int K,
+                     int D, void* stream) {
+    if (!stats || !ema_size || !ema_w || !W || K < 1) return CRK_ERR_ARG;
+    if (D != 64 || (K % 8) != 0 || K > 8192) return CRK_ERR_UNSUPPORTED;
+    if (opblob && (K < 128 || (K % 128) != 0 || K > 512)) return CRK_ERR_UNSUPPORTED;
+    const float one_m_decay = (float)(1.0 - (double)decay);
+    const float keps = (float)((double)K * (double)eps);
+    int* ticket = reinterpret_cast<int*>(stats + (size_t)K + (size_t)K * D);
+    k_vq_ema_fused<<<K / 8, 512, (size_t)K * sizeof(float), (cudaStream_t)stream>>>(stats, stats + K, ema_size, ema_w, W, opblob,
+                                                                                   ticket, decay, one_m_decay, eps, keps, K);
     API_TRY(launch_check());
     return CRK_OK;
 }

@@ -85,6 +85,12 @@ SIGNATURES = {
     "crk_vq_stats_ws_floats": (i64, [i64, i32, i32]),
     "crk_vq_stats": (i32, [vp, i32, vp, vp, vp, vp, i64, i32, i32, vp]),
     "crk_vq_ema": (i32, [vp, vp, vp, vp, vp, f32, f32, i32, i32, vp]),
+    "crk_vq_op_floats": (i64, [i32, i32]),
+    "crk_vq_pack_op": (i32, [vp, vp, i32, i32, vp]),
+    "crk_vq_argmin_fast": (i32, [vp, i32, vp, vp, vp, i32, vp, i32, i64, i32, i32, vp]),
+    "crk_vq_stats_floats": (i64, [i32, i32]),
+    "crk_vq_stats_fused": (i32, [vp, i32, vp, vp, vp, i64, i32, i32, vp]),
+    "crk_vq_ema_fused": (i32, [vp, vp, vp, vp, vp, f32, f32, i32, i32, vp]),
     "crk_vq_scatter_grad": (i32, [vp, i32, vp, vp, i64, i32, i32, vp]),
     "crk_masked_loss_fwd": (i32, [vp, i32, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp]),
     "crk_masked_loss_ws_floats": (i64, [i32, i32, i32]),

@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from .. import _dp
+from ... import lib as L
 from ... import ops
 from ...parallel_wavegan.models import ParallelWaveGANGenerator
 
@@ -191,6 +192,7 @@ class Quantizer(nn.Module):
             self.eps = eps
             self.register_buffer("ema_size", torch.zeros(emb_size))
             self.register_buffer("ema_w", torch.randn(emb_dim, emb_size))
+        self._op_blob, self._op_key = None, None
 
     def forward(self, x, use_ema=True):
         """Reference layout: x (B,D,T) when bdt_flag else (B,T,D) ->
@@ -202,19 +204,36 @@ class Quantizer(nn.Module):
             qx = qx.transpose(1, 2)
         return e, qx, idx
 
+    def _operand_blob(self):
+        """Cached tensor-core operand of the codebook for crk_vq_argmin_fast.  The fused EMA kernel rewrites it together
+        with the codebook; anything else that touches the weight (optimizer step, load_state_dict, init) bumps the
+        tensor version and triggers a re-pack here."""
+        W = self.embedding.weight
+        if not (W.is_cuda and ops.vq_fast_ok(self.emb_size, self.emb_dim)):
+            return None
+        key = (W.data_ptr(), W._version)
+        if self._op_key != key or self._op_blob is None or self._op_blob.device != W.device:
+            reuse = self._op_blob if (self._op_blob is not None and self._op_blob.device == W.device) else None
+            self._op_blob = ops.vq_pack_operand(W, reuse)
+            self._op_key = key
+        return self._op_blob
+
     def forward_cl(self, x, use_ema=True):
         W = self.embedding.weight
         if _dp.active():
             _dp.wait_for([W] + ([self.ema_size, self.ema_w] if self.ema_flag else []))
-        e, qx, idx = ops.VQFn.apply(x, W if not self.ema_flag else W.detach())
+        # a gradient-trained codebook changes through raw-pointer optimizer kernels: pack per call there
+        blob = self._operand_blob() if self.ema_flag else None
+        e, qx, idx = ops.VQFn.apply(x, W if not self.ema_flag else W.detach(), blob)
         if self.training and self.ema_flag and use_ema:
             with torch.no_grad():
-                # data parallel: the [counts | sums] all-reduce and the EMA kernels that follow it go to the
+                # data parallel: the [counts | sums] all-reduce and the EMA kernel that follows it go to the
                 # communication stream; this quantiser's NEXT call (the only reader of the new codebook) waits for them
                 keys = (W, self.ema_size, self.ema_w)
                 ops.vq_ema_update(x.detach(), idx, self.ema_size, self.ema_w, W.data, self.decay,
                                   self.eps, reduce_fn=_dp.stats_reducer(),
-                                  runner=(lambda fn, stats: _dp.run_async(keys, fn, tensors=(stats,))) if _dp.active() else None)
+                                  runner=(lambda fn, stats: _dp.run_async(keys, fn, tensors=(stats,))) if _dp.active() else None,
+                                  opblob=blob)
         return e, qx, idx
 
     def vq(self, x):

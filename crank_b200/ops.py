@@ -127,11 +127,30 @@ class ConvstackFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------
+def vq_fast_ok(K, D):
+    """the round-2 quantiser kernels (crk_vq_fast.cuh): tensor-core modes, D = 64, K in {128, 256, 384, 512}"""
+    return L.get_precision() != "fp32" and D == 64 and K % 128 == 0 and 128 <= K <= 512
+
+
+def vq_pack_operand(W, out=None):
+    """codebook (K, D) -> operand blob of crk_vq_argmin_fast (raw fp32 codebook in the tensor-core layout | |w|^2)"""
+    K, D = W.shape
+    if out is None:
+        out = torch.empty(L.lib().crk_vq_op_floats(K, D), dtype=_f32, device=W.device)
+    Wc = W.detach()
+    L.call("crk_vq_pack_op", L.ptr(Wc if Wc.is_contiguous() else Wc.contiguous()), L.ptr(out), K, D)
+    return out
+
+
 class VQFn(torch.autograd.Function):
-    """idx = argmin L2, e = W[idx], qx = x + (e - x) (straight-through).  crk_vq_argmin."""
+    """idx = argmin L2, e = W[idx], qx = x + (e - x) (straight-through).
+
+    Tensor-core modes: crk_vq_argmin_fast (one TF32 pass + exact fp32 re-score; `opblob` = the caller's cached operand
+    blob of W, packed here when None).  fp32 mode / other shapes: crk_vq_prepare + crk_vq_argmin (CUDA cores).
+    `variant="tf32x3"` selects round 1's crk_vq_argmin_tc (kept for the cross-check tests)."""
 
     @staticmethod
-    def forward(ctx, x, W):
+    def forward(ctx, x, W, opblob=None, variant=None):
         x, ldx = panel(x)
         B, T, D = x.shape
         K = W.shape[0]
@@ -139,21 +158,26 @@ class VQFn(torch.autograd.Function):
         Wc = W.detach()
         if not Wc.is_contiguous():
             Wc = Wc.contiguous()
-        WT = torch.empty(D, K, dtype=_f32, device=dev)
-        wn = torch.empty(K, dtype=_f32, device=dev)
-        L.call("crk_vq_prepare", L.ptr(Wc), L.ptr(WT), L.ptr(wn), K, D)
         idx = torch.empty(B, T, dtype=torch.int64, device=dev)
         e = torch.empty(B, T, D, dtype=_f32, device=dev)
         qx = torch.empty(B, T, D, dtype=_f32, device=dev)
-        if L.get_precision() != "fp32" and D == 64 and K % 128 == 0 and K <= 512:
-            # tensor-core distance GEMM + exact fp32 re-score of near-ties (same indices as the fp32 kernel)
-            blob = torch.empty(L.lib().crk_vq_tc_blob_floats(K, D), dtype=_f32, device=dev)
-            L.call("crk_vq_pack_tc", L.ptr(Wc), L.ptr(blob), K, D)
-            L.call("crk_vq_argmin_tc", L.ptr(x), ldx, L.ptr(Wc), L.ptr(blob), L.ptr(wn), L.ptr(idx),
-                   L.ptr(e), D, L.ptr(qx), D, B * T, K, D)
+        if vq_fast_ok(K, D) and variant is None:
+            if opblob is None:
+                opblob = vq_pack_operand(Wc)
+            L.call("crk_vq_argmin_fast", L.ptr(x), ldx, L.ptr(opblob), L.ptr(idx), L.ptr(e), D, L.ptr(qx), D, B * T, K, D)
         else:
-            L.call("crk_vq_argmin", L.ptr(x), ldx, L.ptr(Wc), L.ptr(WT), L.ptr(wn), L.ptr(idx),
-                   L.ptr(e), D, L.ptr(qx), D, B * T, K, D)
+            WT = torch.empty(D, K, dtype=_f32, device=dev)
+            wn = torch.empty(K, dtype=_f32, device=dev)
+            L.call("crk_vq_prepare", L.ptr(Wc), L.ptr(WT), L.ptr(wn), K, D)
+            if variant == "tf32x3" and D == 64 and K % 128 == 0 and K <= 512:
+                # round 1: 3xTF32 distance GEMM + exact fp32 re-score of near-ties
+                blob = torch.empty(L.lib().crk_vq_tc_blob_floats(K, D), dtype=_f32, device=dev)
+                L.call("crk_vq_pack_tc", L.ptr(Wc), L.ptr(blob), K, D)
+                L.call("crk_vq_argmin_tc", L.ptr(x), ldx, L.ptr(Wc), L.ptr(blob), L.ptr(wn), L.ptr(idx),
+                       L.ptr(e), D, L.ptr(qx), D, B * T, K, D)
+            else:
+                L.call("crk_vq_argmin", L.ptr(x), ldx, L.ptr(Wc), L.ptr(WT), L.ptr(wn), L.ptr(idx),
+                       L.ptr(e), D, L.ptr(qx), D, B * T, K, D)
         ctx.save_for_backward(idx)
         ctx.KD = (K, D)
         ctx.mark_non_differentiable(idx)
@@ -169,28 +193,43 @@ class VQFn(torch.autograd.Function):
             ge, ldg = panel(ge)
             gW = torch.zeros(K, D, dtype=_f32, device=ge.device)
             L.call("crk_vq_scatter_grad", L.ptr(ge), ldg, L.ptr(idx), L.ptr(gW), idx.numel(), K, D)
-        return gx, gW
+        return gx, gW, None, None
 
 
-def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None, runner=None):
+def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None, runner=None, opblob=None):
     """EMA codebook update (vqvae2.py:315-330).  `reduce_fn(flat_stats)` sums [counts | esum]
     across data-parallel ranks before the normalisation; `runner(fn, stats)` may run
-    that reduction and the EMA kernels somewhere else (the communication stream) instead of inline."""
+    that reduction and the EMA kernel somewhere else (the communication stream) instead of inline.
+    D = 64: statistics (2 launches) + ONE fused EMA launch (crk_vq_ema_fused) that also refreshes `opblob`, the
+    operand blob the next crk_vq_argmin_fast call reads."""
     x, ldx = panel(x)
     B, T, D = x.shape
     K = W.shape[0]
     dev = x.device
-    stats = torch.empty(K + D * K, dtype=_f32, device=dev)
     ws = _empty(L.lib().crk_vq_stats_ws_floats(B * T, K, D), dev)
-    counts = stats[:K]
-    esum = stats[K:]
-    L.call("crk_vq_stats", L.ptr(x), ldx, L.ptr(idx), L.ptr(counts), L.ptr(esum), L.ptr(ws),
-           B * T, K, D)
-    def finish():
-        if reduce_fn is not None:
-            reduce_fn(stats)
-        L.call("crk_vq_ema", L.ptr(counts), L.ptr(esum), L.ptr(ema_size), L.ptr(ema_w), L.ptr(W),
-               C.c_float(decay), C.c_float(eps), K, D)
+    if D == 64 and K % 8 == 0:
+        stats = torch.empty(L.lib().crk_vq_stats_floats(K, D), dtype=_f32, device=dev)
+        L.call("crk_vq_stats_fused", L.ptr(x), ldx, L.ptr(idx), L.ptr(stats), L.ptr(ws), B * T, K, D)
+        red = stats[:K + D * K]
+        blob = opblob if (opblob is not None and vq_fast_ok(K, D)) else None
+
+        def finish():
+            if reduce_fn is not None:
+                reduce_fn(red)
+            L.call("crk_vq_ema_fused", L.ptr(stats), L.ptr(ema_size), L.ptr(ema_w), L.ptr(W), L.ptr(blob),
+                   C.c_float(decay), C.c_float(eps), K, D)
+    else:
+        stats = torch.empty(K + D * K, dtype=_f32, device=dev)
+        counts = stats[:K]
+        esum = stats[K:]
+        L.call("crk_vq_stats", L.ptr(x), ldx, L.ptr(idx), L.ptr(counts), L.ptr(esum), L.ptr(ws),
+               B * T, K, D)
+
+        def finish():
+            if reduce_fn is not None:
+                reduce_fn(stats)
+            L.call("crk_vq_ema", L.ptr(counts), L.ptr(esum), L.ptr(ema_size), L.ptr(ema_w), L.ptr(W),
+                   C.c_float(decay), C.c_float(eps), K, D)
 
     if runner is not None:
         runner(finish, stats)

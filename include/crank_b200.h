@@ -192,6 +192,22 @@ int crk_vq_stats(const float* x, int ldx, const long long* idx, float* counts, f
                  float* ws, long long F, int K, int D, void* stream);
 int crk_vq_ema(const float* counts, const float* esum, float* ema_size, float* ema_w, float* W,
                float decay, float eps, int K, int D, void* stream);
+/* Round-2 quantiser path (crk_vq_fast.cuh), same reference code as crk_vq_argmin / crk_vq_ema
+ * (crank/net/module/vqvae2.py:306-347): ONE plain-TF32 tensor-core pass over a codebook that stays resident in shared
+ * memory + exact fp32 re-score of every code inside a rigorous error radius (identical indices to crk_vq_argmin), and
+ * the EMA update in ONE launch that also writes the operand blob of the next call.
+ *   opblob: crk_vq_op_floats(K, D) floats = raw fp32 codebook in the tensor-core operand layout | |w|^2.
+ *   stats : crk_vq_stats_floats(K, D) floats = [counts K | per-code sums D*K (D-major, like ema_w) | ticket].
+ * Data parallel: all-reduce(sum) the first K + D*K floats of `stats` between the two calls. */
+long long crk_vq_op_floats(int K, int D);
+int crk_vq_pack_op(const float* W, float* opblob, int K, int D, void* stream);
+int crk_vq_argmin_fast(const float* x, int ldx, const float* opblob, long long* idx, float* e, int lde, float* qx,
+                       int ldqx, long long F, int K, int D, void* stream);
+long long crk_vq_stats_floats(int K, int D);
+int crk_vq_stats_fused(const float* x, int ldx, const long long* idx, float* stats, float* ws, long long F, int K, int D,
+                       void* stream);
+int crk_vq_ema_fused(float* stats, float* ema_size, float* ema_w, float* W, float* opblob, float decay, float eps, int K,
+                     int D, void* stream);
 /* dW[k][d] += sum_{f: idx[f]=k} g[f][d]  (gradient of the codebook gather; only without EMA) */
 int crk_vq_scatter_grad(const float* g, int ldg, const long long* idx, float* dW, long long F,
                         int K, int D, void* stream);

@@ -104,7 +104,7 @@ class VQEmu:
     """crk_vq_argmin: reference distance expression, first-minimum ties, gather, straight-through."""
 
     @staticmethod
-    def apply(x, W):
+    def apply(x, W, opblob=None, variant=None):
         D = W.shape[1]
         flat = x.reshape(-1, D)
         Wd = W.detach()
@@ -115,7 +115,7 @@ class VQEmu:
         return e, qx, idx
 
 
-def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None, runner=None):
+def vq_ema_update(x, idx, ema_size, ema_w, W, decay, eps, reduce_fn=None, runner=None, opblob=None):
     K, D = W.shape
     onehot = F.one_hot(idx.reshape(-1), K).float()
     stats = torch.cat([onehot.sum(0), (x.reshape(-1, D).T @ onehot).reshape(-1)])

@@ -543,8 +543,13 @@ def test_learnable_stft_windows_train(window):
     n = 1024 + 20 * 128
     wav = 0.2 * torch.randn(2, n, generator=g)
     R = torch.randn(2, 21, 80, generator=g)
-    out = layer(wav.to(_dev()))
-    (out * R.to(_dev())).sum().backward()
+    tf32_was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False      # the "conv" pre-filter is a stock cuDNN conv: keep it in fp32 here
+    try:
+        out = layer(wav.to(_dev()))
+        (out * R.to(_dev())).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32_was
     basis = layer.mlfb_layer.mel_basis.detach().cpu().double()
     if window == "param":
         w = layer.stft_layer.window.detach().cpu().double().requires_grad_(True)

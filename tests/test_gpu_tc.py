@@ -179,27 +179,62 @@ def test_tc_fast_mode_tf32_is_close(precision):
 
 
 def test_tc_vq_argmin_is_identical_to_fp32_kernel(precision):
-    """tensor-core argmin + exact re-score must return the very indices of the fp32 kernel (and e, qx bit-equal),
-    on a spread codebook, on the degenerate fresh-init codebook (all near-ties) and with dead codes (|w|~1e5)."""
+    """tensor-core argmin + exact re-score must return the very indices of the fp32 kernel (and e, qx bit-equal), on a
+    spread codebook, on the degenerate fresh-init codebook (all near-ties) and with dead codes (|w|~1e5): both the round-2
+    kernel (one TF32 pass, resident codebook, persistent CTAs: crk_vq_argmin_fast) and round 1's 3xTF32 kernel."""
     from crank_b200 import ops
 
     g = torch.Generator().manual_seed(31)
-    x = torch.randn(16, 500, 64, generator=g).cuda()
-    for kind in ("spread", "fresh", "dead"):
-        W = torch.randn(512, 64, generator=g)
-        if kind == "fresh":
-            W = (torch.rand(512, 64, generator=g) * 2 - 1) / 512
-        if kind == "dead":
-            W[100:300] *= 1e5
-        W = W.cuda()
-        precision("fp32")
-        e0, q0, i0 = ops.VQFn.apply(x, W)
-        precision("tf32x3")
-        e1, q1, i1 = ops.VQFn.apply(x, W)
-        assert (i1 >= 0).all(), "tcgen05 pipeline timed out"
-        nm = int((i0 != i1).sum())
-        assert nm == 0, f"{kind}: {nm} indices differ between the fp32 and the tensor-core argmin"
-        assert torch.equal(e0, e1) and torch.equal(q0, q1)
+    for B, T, K in ((16, 500, 512), (64, 500, 512), (3, 333, 512), (8, 500, 256), (8, 500, 384), (8, 500, 128)):
+        x = torch.randn(B, T, 64, generator=g).cuda()
+        for kind in ("spread", "fresh", "dead"):
+            W = torch.randn(K, 64, generator=g)
+            if kind == "fresh":
+                W = (torch.rand(K, 64, generator=g) * 2 - 1) / K
+            if kind == "dead":
+                W[K // 5:K // 2] *= 1e5
+            W = W.cuda()
+            precision("fp32")
+            e0, q0, i0 = ops.VQFn.apply(x, W)
+            precision("tf32x3")
+            for variant in (None, "tf32x3"):
+                e1, q1, i1 = ops.VQFn.apply(x, W, None, variant)
+                assert (i1 >= 0).all(), "tcgen05 pipeline timed out"
+                nm = int((i0 != i1).sum())
+                assert nm == 0, f"{kind} {B}x{T} K={K} variant {variant}: {nm} indices differ between the fp32 and the tensor-core argmin"
+                assert torch.equal(e0, e1) and torch.equal(q0, q1)
+
+
+def test_fused_ema_matches_round1_kernels(precision):
+    """crk_vq_stats_fused + crk_vq_ema_fused (one EMA launch, operand blob refreshed in place) against round 1's
+    crk_vq_stats + crk_vq_ema + crk_vq_pack_op: EMA buffers and codebook bit-identical, blob bit-identical to a fresh pack."""
+    import ctypes as C
+
+    from crank_b200 import lib as L
+    from crank_b200 import ops
+
+    precision("tf32x3")
+    g = torch.Generator().manual_seed(5)
+    K, D = 512, 64
+    x = torch.randn(8, 500, D, generator=g).cuda()
+    W = torch.randn(K, D, generator=g).cuda()
+    size = torch.rand(K, generator=g).cuda() * 10
+    emaw = torch.randn(D, K, generator=g).cuda()
+    _, _, idx = ops.VQFn.apply(x, W)
+    # round 1 sequence
+    W1, s1, w1 = W.clone(), size.clone(), emaw.clone()
+    stats = torch.empty(K + D * K, device="cuda")
+    ws = torch.empty(L.lib().crk_vq_stats_ws_floats(x.shape[0] * x.shape[1], K, D), device="cuda")
+    L.call("crk_vq_stats", L.ptr(x), D, L.ptr(idx), L.ptr(stats[:K]), L.ptr(stats[K:]), L.ptr(ws), x.shape[0] * x.shape[1], K, D)
+    L.call("crk_vq_ema", L.ptr(stats[:K]), L.ptr(stats[K:]), L.ptr(s1), L.ptr(w1), L.ptr(W1), C.c_float(0.99), C.c_float(1e-5), K, D)
+    # round 2
+    W2, s2, w2 = W.clone(), size.clone(), emaw.clone()
+    blob = ops.vq_pack_operand(W2)
+    for _ in range(2):      # twice: the ticket counter must reset itself
+        W2.copy_(W); s2.copy_(size); w2.copy_(emaw)
+        ops.vq_ema_update(x, idx, s2, w2, W2, 0.99, 1e-5, opblob=blob)
+        assert torch.equal(s1, s2) and torch.equal(w1, w2) and torch.equal(W1, W2)
+        assert torch.equal(blob, ops.vq_pack_operand(W2))
 
 
 @pytest.mark.parametrize("in_ch,out_ch,aux,k,layers,stacks,causal,B,T", [_STACKS[0], _STACKS[2], _STACKS[3], _STACKS[5]])
