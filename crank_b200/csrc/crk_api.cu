@@ -325,7 +325,8 @@ int crk_vq_argmin_fast(const float* x, int ldx, const float* opblob, long long* 
     q.opblob = opblob;
     static bool attr_set = false;
     if (!attr_set) {
-        API_TRY(cudaFuncSetAttribute(k_vq_argmin_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        // (dynamic + ~3 KB of static shared memory must stay below the 227 KB per-CTA limit)
+        API_TRY(cudaFuncSetAttribute(k_vq_argmin_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vq_fast_smem(512)));
         attr_set = true;
     }
     const long long tiles = cdivl(F, 128);

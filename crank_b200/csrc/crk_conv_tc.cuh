@@ -34,18 +34,19 @@ struct ConvTcParams {
 // A-tile staging of the gate-backward mode: 128 rows x 128 interleaved [sqrt(.5)*dH | dS] columns
 // KEEP: the staged values stay in `keep` (one round: U * 256 == 128 * 32) and the GOS global store is issued
 // later by the caller, overlapped with the MMAs, instead of competing with the dH / dS loads here
+// pshift / q0: the pairs [q0, q0 + (1 << pshift)) are staged (a K phase of the 2-CTA/SM variant: 16 pairs; all: 32)
 template <bool SPLIT, int U, bool KEEP>
 __device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats, const ConvTcParams& q, int b, int t0,
-                                             float4 (&keep)[KEEP ? U : 1]) {
+                                             float4 (&keep)[KEEP ? U : 1], int pshift = 5, int q0 = 0) {
     const ConvParams& p = q.p;
-    const int total = CRK_TC_TM * 32;                      // (row, pair q): one float4 of A each
+    const int total = CRK_TC_TM << pshift;                 // (row, pair q): one float4 of A each
     for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
         float2 h[U], sg[U];
         int rr[U], qq[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int idx = base + u * blockDim.x;
-            rr[u] = idx >> 5; qq[u] = idx & 31;
+            rr[u] = idx >> pshift; qq[u] = q0 + (idx & ((1 << pshift) - 1));
             h[u] = make_float2(0.f, 0.f); sg[u] = make_float2(0.f, 0.f);
             const int t = t0 + rr[u];
             if (idx < total && t < p.T) {
@@ -62,7 +63,7 @@ __device__ __forceinline__ void tc_stage_gos(float* hi, float* lo, int cs_floats
             const int t = t0 + rr[u];
             if (KEEP) keep[KEEP ? u : 0] = v;
             else if (t < p.T) reinterpret_cast<float4*>(q.g_GOS + ((size_t)b * p.T + t) * 128)[qq[u]] = v;
-            const int off = qq[u] * cs_floats + rr[u] * 4;  // chunk = pair index (4 interleaved columns)
+            const int off = (qq[u] - q0) * cs_floats + rr[u] * 4;  // chunk = pair index (4 interleaved columns)
             if (SPLIT) {
                 float4 hh, ll;
                 tc::split_tf32(v.x, hh.x, ll.x); tc::split_tf32(v.y, hh.y, ll.y);
@@ -123,10 +124,11 @@ __device__ __forceinline__ void tc_stage_gos4(float* hi, float* lo, int cs_float
     }
 }
 
+// cbeg / c4n_sel: only the channel chunks [cbeg, cbeg + c4n_sel) are staged, at chunk offset 0 of the tile (a K phase)
 template <bool SPLIT, int U, bool HASMUL, bool VECONLY>
 __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_floats, const ConvParams& p, int Kpad,
-                                                 int b, int tstart, int rows, int c4shift = -1) {
-    const int c4n = Kpad >> 2;
+                                                 int b, int tstart, int rows, int c4shift = -1, int cbeg = 0, int c4n_sel = -1) {
+    const int c4n = c4n_sel >= 0 ? c4n_sel : (Kpad >> 2);
     const int total = rows * c4n;
     const bool vec = VECONLY ||
                      (((p.ldx & 3) == 0) && ((p.Cin & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
@@ -144,8 +146,9 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
             if (HASMUL) m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
             off[u] = -1;
             if (idx < total) {
-                const int r = (VECONLY && c4shift >= 0) ? (idx >> c4shift) : idx / c4n, c4 = idx - r * c4n;
-                off[u] = c4 * cs_floats + r * 4;
+                const int r = (VECONLY && c4shift >= 0) ? (idx >> c4shift) : idx / c4n, cl = idx - r * c4n;
+                const int c4 = cbeg + cl;
+                off[u] = cl * cs_floats + r * 4;
                 const int tt = tstart + r;
                 const int c = c4 * 4;
                 if (tt >= 0 && tt < p.T && c < p.Cin) {
@@ -198,19 +201,24 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
 #define CRK_CONV_GENERIC 0
 #define CRK_CONV_GATE 1
 #define CRK_CONV_FAST 2
+// K PHASES (round 2).  Round 1 staged the whole K (up to 128 channels, hi | lo = 140 KB for the dgrad tile) at once, which
+// left room for ONE CTA per SM: 256 tiles on 148 SMs ran as two strictly serial waves whose global-memory phases
+// (staging, epilogue) hit HBM in lock step while the tensor pipe idled, and vice versa.  Now a CTA stages at most
+// PHC = 16 channel chunks (64 channels) at a time and the weight ring holds SEG = 8 chunks per slot: 70 + 33 KB, two
+// CTAs per SM (and <= 128 registers), so one CTA's MMAs run under the other's staging / epilogue and every tile of a
+// 64 x 500-frame launch is resident in a single wave.  Phase ph: wait until the MMAs of phase ph-1 have read the A tile,
+// restage, issue (tap, segment) steps; the weight producer runs NSLOT steps ahead across phase boundaries.
 template <bool SPLIT, int MODE>
-__global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcParams q) {
+__global__ void __launch_bounds__(256, 2) k_conv_tc(const ConvTcParams q) {
     const ConvParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
-    // weight ring: NSLOT slots of SEG K-chunks (SEG * 4 channels).  Measured: 4 slots x 32 channels is SLOWER
-    // than 2 x 64 (dgrad k5: MMA phase 32K vs 27K cycles) -- the per-step cost (barrier round trip, pass
-    // prologues of the issue loop) outweighs the deeper prefetch; the weight bytes are not the bottleneck
-    // (issuer wait for weights: 3K of the 27K cycles).
-    constexpr int NSLOT = 2, SEG = 16;
+    constexpr int NSLOT = 2;
+    constexpr int SEG = SPLIT ? 8 : 16;            // channel chunks per ring slot
+    constexpr int PHC = SPLIT ? 16 : 32;           // channel chunks staged per K phase
     __shared__ uint64_t bar_full[NSLOT];
     __shared__ uint64_t bar_free[NSLOT];
-    __shared__ uint64_t bar_acc;
+    __shared__ uint64_t bar_acc;                   // all MMAs of a phase have completed (one completion per phase)
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
@@ -221,24 +229,33 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     const int csx = tc::chunk_rows(rowsX) * 4;                 // floats per A chunk
     const int kch = q.Kpad >> 2;                               // A / B chunks over the whole K
     const int csw = tc::chunk_rows(q.Npad) * 4;                // floats per B chunk
-    const int nseg = (kch + SEG - 1) / SEG;                    // 32-channel K segments
+    const int nph = (kch + PHC - 1) / PHC;                     // K phases
+    const int phc_max = kch < PHC ? kch : PHC;
     const int whalf_tap = kch * csw;                           // floats of the hi half of one tap blob
     const int seg_max = (kch < SEG ? kch : SEG) * csw;         // floats of one segment half in a slot
     float* Xh = smem;
-    float* Xl = Xh + kch * csx;
-    float* ring = Xl + (SPLIT ? kch * csx : 0);
+    float* Xl = Xh + phc_max * csx;
+    float* ring = Xl + (SPLIT ? phc_max * csx : 0);
     auto slot_hi = [&](int sl) -> float* { return ring + sl * (SPLIT ? 2 : 1) * seg_max; };
     auto slot_lo = [&](int sl) -> float* { return ring + sl * (SPLIT ? 2 : 1) * seg_max + seg_max; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nsteps = p.k * nseg;
+    auto ph_chunks = [&](int ph) -> int { const int r = kch - ph * PHC; return r < PHC ? r : PHC; };
+    auto ph_nseg = [&](int ph) -> int { return (ph_chunks(ph) + SEG - 1) / SEG; };
+    // steps are enumerated phase-major: (ph, tap j, segment sg);  steps_before(ph) = first step index of phase ph
+    auto steps_before = [&](int ph) -> int { int n = 0; for (int i = 0; i < ph; ++i) n += p.k * ph_nseg(i); return n; };
+    const int nsteps = steps_before(nph);
 
-    // step -> (tap j, K segment sg): TMA bulk copy of that slice of the tap's blob into a ring slot
-    auto produce = [&](int step) {
-        const int j = step / nseg, sg = step - j * nseg;
-        const int ch0 = sg * SEG;
-        const int nch = (kch - ch0) < SEG ? (kch - ch0) : SEG;
+    // TMA bulk copy of step st's weight slice into its ring slot
+    auto produce = [&](int st) {
+        int ph = 0, rem = st;
+        while (rem >= p.k * ph_nseg(ph)) { rem -= p.k * ph_nseg(ph); ++ph; }
+        const int ns = ph_nseg(ph);
+        const int j = rem / ns, sg = rem - j * ns;
+        const int ch0 = ph * PHC + sg * SEG;
+        const int chend = ph * PHC + ph_chunks(ph);
+        const int nch = (chend - ch0) < SEG ? (chend - ch0) : SEG;
         const float* blob = q.Wtc + (size_t)j * 2 * whalf_tap + (size_t)ch0 * csw;
-        const int sl = step & (NSLOT - 1);
+        const int sl = st & (NSLOT - 1);
         tc_bulk_blob<SPLIT>(slot_hi(sl), slot_lo(sl), blob, nch * csw, whalf_tap, &bar_full[sl]);
     };
 
@@ -257,70 +274,68 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     pdl_trigger();                                      // only now: this CTA already owns its TMEM columns (see crk_common.cuh)
     pdl_wait();
     dbg_stamp(q.dbg, 0);
+    int produced = 0;                                   // (meaningful in thread 0 only)
     if (threadIdx.x == 0)
-        for (int st = 0; st < NSLOT && st < nsteps; ++st) produce(st);
-    // (deeper batches were measured: no gain in the 3xTF32 mode, and the extra registers cost the plain
-    //  TF32 variant its second resident CTA per SM, which matters far more)
-    // the whole A tile in ONE batch of independent loads when the registers allow (3xTF32 variant: one CTA
-    // per SM, 255 registers): a batch costs ~2.4K cycles however many loads it holds (measured: 5 batches
-    // of 4 = 12K cycles for the K=128 dgrad tile)
-    // gate mode, 3xTF32 variant (one CTA per SM, registers to spare): the staged [sqrt(.5) dH | dS] values stay in
-    // registers; their GOS store and the TaSb loads of the epilogue are issued while the MMAs run
-    constexpr bool GATE_OVERLAP = (MODE == CRK_CONV_GATE) && SPLIT;
-    float4 gkeep[GATE_OVERLAP ? 16 : 1];
-    float4 gts[GATE_OVERLAP ? 16 : 1];
-    if constexpr (GATE_OVERLAP) tc_stage_gos4<SPLIT>(Xh, Xl, csx, q, b, t0, gkeep);
-    else if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, 4, false>(Xh, Xl, csx, q, b, t0, gkeep);
-    else if constexpr (MODE == CRK_CONV_FAST) tc_stage_act_pro<SPLIT, (SPLIT ? 9 : 5), false, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX, q.kshift);
-    else tc_stage_act_pro<SPLIT, 4, true, false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX);
-    tc::fence_proxy_async_smem();
-    __syncthreads();
-    dbg_stamp(q.dbg, 1);
-
-    // one elected lane per role; the other 31 lanes of that warp park at __syncwarp (no spinning next to
-    // the working lane)
-    if (warp == 0) {
-        if (lane == 0) {
-            long long wfree = 0;
-            for (int st = NSLOT; st < nsteps; ++st) {
-                const long long c0 = q.dbg ? clock64() : 0;
-                ok &= tc::mbar_wait(&bar_free[st & (NSLOT - 1)], ((st - NSLOT) / NSLOT) & 1);
-                if (q.dbg) wfree += clock64() - c0;
-                produce(st);
-            }
-            dbg_put(q.dbg, 9, wfree);
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues (see tc_issue_kmajor_w)
-        const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
-        const uint32_t xh_s = tc::smem_u32(Xh), xl_s = tc::smem_u32(Xl);
-        uint32_t acc = 0;
-        long long wfull = 0;
-        for (int st = 0; st < nsteps; ++st) {
-            const int j = st / nseg, sg = st - j * nseg;
-            const int ch0 = sg * SEG;
-            const int nch = (kch - ch0) < SEG ? (kch - ch0) : SEG;
-            const int sl = st & (NSLOT - 1);
-            const long long c0 = q.dbg ? clock64() : 0;
-            ok &= tc::mbar_wait(&bar_full[sl], (st / NSLOT) & 1);
-            if (q.dbg) wfull += clock64() - c0;
+        for (; produced < NSLOT && produced < nsteps; ++produced) produce(produced);
+    float4 gkeep[1];
+    const uint32_t idesc = tc::make_idesc_tf32(128, q.Npad, 0, 0);
+    uint32_t acc = 0;
+    long long wfull = 0, wfree = 0;
+    for (int ph = 0; ph < nph; ++ph) {
+        const int pc0 = ph * PHC, pcn = ph_chunks(ph);
+        if (ph > 0) {                                   // the MMAs of the previous phase have read the A tile
+            ok &= tc::mbar_wait(&bar_acc, (ph - 1) & 1);
             tc::tc_fence_after();
-            tc_issue_kmajor_w<SPLIT>(tmem, xh_s + ch0 * csx * 4, xl_s + ch0 * csx * 4, csx * 4, j * p.dil,
-                                     tc::smem_u32(slot_hi(sl)), tc::smem_u32(slot_lo(sl)), csw * 4,
-                                     nch * 4, idesc, acc);
-            if (tc::elect_one()) tc::umma_commit(&bar_free[sl]);
         }
-        if (tc::elect_one()) tc::umma_commit(&bar_acc);
-        if (lane == 0) dbg_put(q.dbg, 8, wfull);
-        __syncwarp();
+        if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, 4, false>(Xh, Xl, csx, q, b, t0, gkeep, SPLIT ? 4 : 5, pc0);
+        else if constexpr (MODE == CRK_CONV_FAST)
+            tc_stage_act_pro<SPLIT, 4, false, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX,
+                                                    (pcn == 16) ? 4 : ((pcn == 32) ? 5 : ((pcn == 8) ? 3 : -1)), pc0, pcn);
+        else tc_stage_act_pro<SPLIT, 4, true, false>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX, -1, pc0, pcn);
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (ph == 0) dbg_stamp(q.dbg, 1);
+        const int st0 = steps_before(ph), st1 = st0 + p.k * ph_nseg(ph);
+        // one elected lane per role; the other 31 lanes of that warp park at __syncwarp
+        if (warp == 0) {
+            if (lane == 0) {
+                const int upto = (st1 + NSLOT) < nsteps ? (st1 + NSLOT) : nsteps;       // runs NSLOT steps into the next phase
+                for (; produced < upto; ++produced) {
+                    const long long c0 = q.dbg ? clock64() : 0;
+                    ok &= tc::mbar_wait(&bar_free[produced & (NSLOT - 1)], ((produced - NSLOT) / NSLOT) & 1);
+                    if (q.dbg) wfree += clock64() - c0;
+                    produce(produced);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues (see tc_issue_kmajor_w)
+            const uint32_t xh_s = tc::smem_u32(Xh), xl_s = tc::smem_u32(Xl);
+            const int ns = ph_nseg(ph);
+            for (int st = st0; st < st1; ++st) {
+                const int rem = st - st0;
+                const int j = rem / ns, sg = rem - j * ns;
+                const int cl0 = sg * SEG;                               // first chunk of the segment inside the staged tile
+                const int nch = (pcn - cl0) < SEG ? (pcn - cl0) : SEG;
+                const int sl = st & (NSLOT - 1);
+                const long long c0 = q.dbg ? clock64() : 0;
+                ok &= tc::mbar_wait(&bar_full[sl], (st / NSLOT) & 1);
+                if (q.dbg) wfull += clock64() - c0;
+                tc::tc_fence_after();
+                tc_issue_kmajor_w<SPLIT>(tmem, xh_s + cl0 * csx * 4, xl_s + cl0 * csx * 4, csx * 4, j * p.dil,
+                                         tc::smem_u32(slot_hi(sl)), tc::smem_u32(slot_lo(sl)), csw * 4,
+                                         nch * 4, idesc, acc);
+                if (tc::elect_one()) tc::umma_commit(&bar_free[sl]);
+            }
+            if (tc::elect_one()) tc::umma_commit(&bar_acc);
+            __syncwarp();
+        }
     }
+    if (threadIdx.x == 0) dbg_put(q.dbg, 9, wfree);
+    if (threadIdx.x == 32) dbg_put(q.dbg, 8, wfull);
     // FAST mode: side inputs of the epilogue (residual gradient, dropout multiplier, activation-derivative
-    // source, old output) -- U float4 each.  Fetching the first round here, under the MMAs, was measured SLOWER
-    // (conv family 7.2 -> 7.7 ms per step: the loads contend with the weight stream and lengthen the MMA
-    // phase by more than the epilogue saves), unlike the gate mode's TaSb prefetch below; kept switchable.
-    constexpr bool EPI_PRE = false;
-    constexpr int EU = (MODE == CRK_CONV_FAST) ? (SPLIT ? 8 : 4) : 1;
+    // source, old output) -- EU float4 each, fetched after the accumulator wait.
+    constexpr int EU = (MODE == CRK_CONV_FAST) ? 4 : 1;
     float4 mulv[EU], rv[EU], dv[EU], oldv[EU];
     auto epi_side_load = [&](int e0) {
         const int c4n = p.Cout >> 2;
@@ -341,25 +356,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
             }
         }
     };
-    if constexpr (EPI_PRE) epi_side_load(threadIdx.x);
-    if constexpr (GATE_OVERLAP) {
-        const size_t row0g = (size_t)b * p.T + t0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {                       // same (row, channel quad) items as tc_stage_gos4
-            const int idx = threadIdx.x + u * 256, rr = idx >> 4, pp = idx & 15;
-            if (t0 + rr < p.T) {
-                float4* dst = reinterpret_cast<float4*>(q.g_GOS + (row0g + rr) * 128) + 2 * pp;
-                dst[0] = gkeep[2 * u]; dst[1] = gkeep[2 * u + 1];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int e = threadIdx.x + u * 256, rr = e >> 5, qi = e & 31;
-            gts[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t0 + rr < p.T) gts[u] = __ldg(reinterpret_cast<const float4*>(q.g_TaSb + (row0g + rr) * 128) + qi);
-        }
-    }
-    ok &= tc::mbar_wait(&bar_acc, 0);
+    ok &= tc::mbar_wait(&bar_acc, (nph - 1) & 1);
     tc::tc_fence_after();
     if (!ok) timeout_s = 1;
     dbg_stamp(q.dbg, 2);
@@ -383,23 +380,7 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
     }
     __syncthreads();
     dbg_stamp(q.dbg, 3);
-    if constexpr (GATE_OVERLAP) {
-        const size_t row0 = (size_t)b * p.T + t0;
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int e = threadIdx.x + u * 256, rr = e >> 5, qi = e & 31;
-            if (t0 + rr >= p.T) continue;
-            const float4 ts = gts[u];
-            const float dz0 = S[rr * sst + 2 * qi], dz1 = S[rr * sst + 2 * qi + 1];
-            float4 dg;                                  // same expressions as the non-overlapped path below
-            dg.x = (dz0 * ts.z) * (1.f - ts.x * ts.x);
-            dg.y = (dz1 * ts.w) * (1.f - ts.y * ts.y);
-            dg.z = (dz0 * ts.x) * ((1.f - ts.z) * ts.z);
-            dg.w = (dz1 * ts.y) * ((1.f - ts.w) * ts.w);
-            reinterpret_cast<float4*>(q.g_DG + (row0 + rr) * 128)[qi] = dg;
-            reinterpret_cast<float2*>(q.g_Z + (row0 + rr) * 64)[qi] = make_float2(ts.x * ts.z, ts.y * ts.w);
-        }
-    } else if constexpr (MODE == CRK_CONV_GATE) {
+    if constexpr (MODE == CRK_CONV_GATE) {
         // lanes over gate pairs (2 z channels each): TaSb read and DG write are one float4 per lane
         const int nlive = min(CRK_TC_TM, p.T - t0);
         const size_t row0 = (size_t)b * p.T + t0;
@@ -435,10 +416,9 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
         const size_t row0 = (size_t)b * p.T + t0;
         const int c4n = p.Cout >> 2;
         const int total = nlive * c4n;
-        constexpr int U = SPLIT ? 8 : 4;                    // (the 2-CTA/SM plain-TF32 variant is capped at 128 registers)
+        constexpr int U = 4;                                // (two CTAs per SM: 128 registers per thread)
         for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * U) {
-            // round 0 of the 3xTF32 variant was loaded while the MMAs ran (epi_side_load before the accumulator wait)
-            if (!(EPI_PRE && e0 == (int)threadIdx.x)) epi_side_load(e0);
+            epi_side_load(e0);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int e = e0 + u * blockDim.x;
@@ -515,8 +495,9 @@ __global__ void __launch_bounds__(256, SPLIT ? 1 : 2) k_conv_tc(const ConvTcPara
 inline size_t conv_tc_smem(const ConvTcParams& q, bool split) {
     const int rowsX = CRK_TC_TM + (q.p.k - 1) * q.p.dil;
     const int kch = q.Kpad >> 2;
-    const size_t a = (size_t)kch * tc::chunk_rows(rowsX) * 4;
-    const size_t seg = (size_t)(kch < 16 ? kch : 16) * tc::chunk_rows(q.Npad) * 4;     // 2 ring slots of 16 chunks
+    const int phc = split ? 16 : 32, segc = split ? 8 : 16;             // PHC / SEG of the kernel
+    const size_t a = (size_t)(kch < phc ? kch : phc) * tc::chunk_rows(rowsX) * 4;
+    const size_t seg = (size_t)(kch < segc ? kch : segc) * tc::chunk_rows(q.Npad) * 4;   // one half of a ring slot
     const size_t pipe = (split ? 2 : 1) * a + (split ? 4 : 2) * seg;
     const size_t stage = (size_t)CRK_TC_TM * (q.Npad | 1);      // epilogue transposition tile
     return (pipe > stage ? pipe : stage) * sizeof(float);

@@ -136,7 +136,7 @@ def vq_pack_operand(W, out=None):
     """codebook (K, D) -> operand blob of crk_vq_argmin_fast (raw fp32 codebook in the tensor-core layout | |w|^2)"""
     K, D = W.shape
     if out is None:
-        out = torch.empty(L.lib().crk_vq_op_floats(K, D), dtype=_f32, device=W.device)
+        out = torch.zeros(L.lib().crk_vq_op_floats(K, D), dtype=_f32, device=W.device)    # (pad rows stay 0)
     Wc = W.detach()
     L.call("crk_vq_pack_op", L.ptr(Wc if Wc.is_contiguous() else Wc.contiguous()), L.ptr(out), K, D)
     return out

@@ -233,8 +233,10 @@ def test_fused_ema_matches_round1_kernels(precision):
     for _ in range(2):      # twice: the ticket counter must reset itself
         W2.copy_(W); s2.copy_(size); w2.copy_(emaw)
         ops.vq_ema_update(x, idx, s2, w2, W2, 0.99, 1e-5, opblob=blob)
-        assert torch.equal(s1, s2) and torch.equal(w1, w2) and torch.equal(W1, W2)
-        assert torch.equal(blob, ops.vq_pack_operand(W2))
+        assert torch.equal(s1, s2), f"ema_size differs: {(s1 - s2).abs().max().item():.3e}"
+        assert torch.equal(w1, w2), f"ema_w differs: {(w1 - w2).abs().max().item():.3e}"
+        assert torch.equal(W1, W2), f"codebook differs: {(W1 - W2).abs().max().item():.3e}"
+        assert torch.equal(blob, ops.vq_pack_operand(W2)), "operand blob differs from a fresh pack"
 
 
 @pytest.mark.parametrize("in_ch,out_ch,aux,k,layers,stacks,causal,B,T", [_STACKS[0], _STACKS[2], _STACKS[3], _STACKS[5]])
