@@ -71,6 +71,8 @@ inline int& tc_disable_mask() { static int m = 0; return m; }
 //   4 k_conv_tc FAST instance (128-bit staging + epilogue) off -> GENERIC instance, 8 raw-tile k_wgrad_tc_raw off,
 //   16 persistent pipelined fused forward (k_resblock_fwd_pt) off -> k_resblock_fwd_tc,
 //   32 persistent pipelined conv / dgrad (k_conv_pt) off -> k_conv_tc
+//   64 two-CTA/SM fused forward (k_resblock_fwd_tc2) off -> round 1's k_resblock_fwd_tc
+//   128 two-CTA/SM K-phased k_conv_tc off -> whole-K variant (one CTA per SM in the 3xTF32 mode)
 inline int& opt_disable_mask() { static int m = 0; return m; }
 // opt-IN switches (crk_debug_opt_enable / CRANK_B200_OPT_ENABLE): experimental paths that are correct (parity-tested)
 // but not yet faster than the default ones:

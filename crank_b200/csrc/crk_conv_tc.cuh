@@ -208,14 +208,16 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
 // CTAs per SM (and <= 128 registers), so one CTA's MMAs run under the other's staging / epilogue and every tile of a
 // 64 x 500-frame launch is resident in a single wave.  Phase ph: wait until the MMAs of phase ph-1 have read the A tile,
 // restage, issue (tap, segment) steps; the weight producer runs NSLOT steps ahead across phase boundaries.
-template <bool SPLIT, int MODE>
-__global__ void __launch_bounds__(256, 2) k_conv_tc(const ConvTcParams q) {
+// WIDE: round 1's footprint (whole K staged at once, 16-chunk ring slots, one CTA per SM in the 3xTF32 mode) -- the shorter
+// per-CTA latency wins when the launch has no more tiles than SMs (8 utterances per GPU: 32 tiles), where nothing can co-reside.
+template <bool SPLIT, int MODE, bool WIDE>
+__global__ void __launch_bounds__(256, (SPLIT && WIDE) ? 1 : 2) k_conv_tc(const ConvTcParams q) {
     const ConvParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
     constexpr int NSLOT = 2;
-    constexpr int SEG = SPLIT ? 8 : 16;            // channel chunks per ring slot
-    constexpr int PHC = SPLIT ? 16 : 32;           // channel chunks staged per K phase
+    constexpr int SEG = (SPLIT && !WIDE) ? 8 : 16;     // channel chunks per ring slot
+    constexpr int PHC = (SPLIT && !WIDE) ? 16 : 32;    // channel chunks staged per K phase
     __shared__ uint64_t bar_full[NSLOT];
     __shared__ uint64_t bar_free[NSLOT];
     __shared__ uint64_t bar_acc;                   // all MMAs of a phase have completed (one completion per phase)
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc(const ConvTcParams q) {
             ok &= tc::mbar_wait(&bar_acc, (ph - 1) & 1);
             tc::tc_fence_after();
         }
-        if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, 4, false>(Xh, Xl, csx, q, b, t0, gkeep, SPLIT ? 4 : 5, pc0);
+        if constexpr (MODE == CRK_CONV_GATE) tc_stage_gos<SPLIT, 4, false>(Xh, Xl, csx, q, b, t0, gkeep, PHC == 16 ? 4 : 5, pc0);
         else if constexpr (MODE == CRK_CONV_FAST)
             tc_stage_act_pro<SPLIT, 4, false, true>(Xh, Xl, csx, p, q.Kpad, b, t0 - p.padl, rowsX,
                                                     (pcn == 16) ? 4 : ((pcn == 32) ? 5 : ((pcn == 8) ? 3 : -1)), pc0, pcn);
@@ -492,10 +494,10 @@ __global__ void __launch_bounds__(256, 2) k_conv_tc(const ConvTcParams q) {
     if (warp == 1) tc::tmem_dealloc<128>(tmem);
 }
 
-inline size_t conv_tc_smem(const ConvTcParams& q, bool split) {
+inline size_t conv_tc_smem(const ConvTcParams& q, bool split, bool wide = false) {
     const int rowsX = CRK_TC_TM + (q.p.k - 1) * q.p.dil;
     const int kch = q.Kpad >> 2;
-    const int phc = split ? 16 : 32, segc = split ? 8 : 16;             // PHC / SEG of the kernel
+    const int phc = (split && !wide) ? 16 : 32, segc = (split && !wide) ? 8 : 16;     // PHC / SEG of the kernel
     const size_t a = (size_t)(kch < phc ? kch : phc) * tc::chunk_rows(rowsX) * 4;
     const size_t seg = (size_t)(kch < segc ? kch : segc) * tc::chunk_rows(q.Npad) * 4;   // one half of a ring slot
     const size_t pipe = (split ? 2 : 1) * a + (split ? 4 : 2) * seg;
@@ -506,12 +508,20 @@ inline bool conv_tc_ok(const ConvTcParams& q, bool split) {
     return q.Wtc != nullptr && q.Npad >= 16 && q.Npad <= 128 && (q.Npad % 16) == 0 && q.Kpad >= 8 && q.Kpad <= 128 &&
            (q.p.k - 1) * q.p.dil <= 32 && conv_tc_smem(q, split) <= 220 * 1024;
 }
+inline int device_sm_count_conv() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
 
-template <bool SPLIT, int MODE>
-inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
+template <bool SPLIT, int MODE, bool WIDE>
+inline cudaError_t launch_conv_tc_w(const ConvTcParams& q, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv_tc<SPLIT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_conv_tc<SPLIT, MODE, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -520,9 +530,17 @@ inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
                    MODE == CRK_CONV_GATE ? 2.0 * q.p.B * q.p.T * 128.0 * 64 : 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.Cout * q.p.k);
     ConvTcParams qq = q;
     qq.dbg = dbg_take(MODE == CRK_CONV_GATE ? CRK_K_BWD_GATE : CRK_K_CONV);
-    cudaError_t le = launch_pdl(k_conv_tc<SPLIT, MODE>, dim3(tiles), dim3(256), conv_tc_smem(q, SPLIT), s, qq);
+    cudaError_t le = launch_pdl(k_conv_tc<SPLIT, MODE, WIDE>, dim3(tiles), dim3(256), conv_tc_smem(q, SPLIT, WIDE), s, qq);
     if (le != cudaSuccess) return le;
     return launch_check();
+}
+template <bool SPLIT, int MODE>
+inline cudaError_t launch_conv_tc_t(const ConvTcParams& q, cudaStream_t s) {
+    const int tiles = q.p.B * cdiv(q.p.T, CRK_TC_TM);
+    // 3xTF32: the two-CTA/SM footprint pays when tiles outnumber SMs; otherwise the whole-K variant has the shorter latency
+    if (SPLIT && (tiles <= device_sm_count_conv() || (opt_disable_mask() & 128)) && conv_tc_smem(q, true, true) <= 220 * 1024)
+        return launch_conv_tc_w<SPLIT, MODE, true>(q, s);
+    return launch_conv_tc_w<SPLIT, MODE, false>(q, s);
 }
 
 // persistent pipelined variant (crk_conv_pt.cuh, included after this header)

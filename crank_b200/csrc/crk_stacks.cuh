@@ -9,6 +9,7 @@
 #include "crk_resblock.cuh"
 #include "crk_resblock_tc.cuh"
 #include "crk_resblock_pt.cuh"
+#include "crk_resblock_tc2.cuh"
 #include "crk_conv_tc.cuh"
 #include "crk_conv_pt.cuh"
 #include "crk_wgrad_tc.cuh"
@@ -297,6 +298,10 @@ inline int wavenet_fwd(const crk_wavenet_cfg* c, const float* weff, const float*
             if ((opt_enable_mask() & 1) && resblock_fwd_pt_ok(q, split)) {       // persistent pipelined kernel (round 2)
                 if (split) CRK_TRY(launch_resblock_fwd_pt<true>(q, s));
                 else CRK_TRY(launch_resblock_fwd_pt<false>(q, s));
+            } else if (!(opt_disable_mask() & 64) && resblock_fwd_tc2_ok(q, split) &&
+                       B * cdiv(T, CRK_TC_TM) > device_sm_count()) {   // 2-CTA/SM kernel (round 2): pays when tiles outnumber SMs
+                if (split) CRK_TRY(launch_resblock_fwd_tc2<true>(q, s));
+                else CRK_TRY(launch_resblock_fwd_tc2<false>(q, s));
             } else if (split) CRK_TRY(launch_resblock_fwd_tc<true>(q, s));
             else CRK_TRY(launch_resblock_fwd_tc<false>(q, s));
         }

@@ -76,6 +76,9 @@ class GraphedTrainStep:
             with torch.cuda.stream(side):                      # THIS call's step runs eagerly, on a side stream
                 eager_values = t._parse_loss(t._train_core(static, self.phase))     # (torch's capture warm-up rule)
             torch.cuda.current_stream().wait_stream(side)
+            from . import _dp
+
+            _dp.flush()          # data parallel: no completion event of the eager steps' side-stream work may be waited on inside the capture
             self._drop_weight_caches()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
