@@ -49,8 +49,8 @@ def parse():
                     help="utterances per step of the CPU arms (0 = the same batch as the GPU arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
-                    help="EXPERIMENTAL (not yet validated on hardware): replay the step from a whole-step CUDA graph "
-                         "(crank_b200/net/graph.py); lsgan / vqvae trainers only")
+                    help="replay the step from a whole-step CUDA graph (crank_b200/net/graph.py; validated bit-identical to "
+                         "the eager step in tests/test_gpu_graph.py); lsgan / vqvae trainers only")
     ap.add_argument("--no-eager-gpu-baseline", action="store_true",
                     help="skip timing the reference's own graph (the oracle port under stock PyTorch eager: cuDNN / "
                          "cuBLAS) on this GPU at the bench batch -- SURVEY.md section 8d's 'reference GPU path' bar, "
@@ -212,17 +212,21 @@ class ClockSampler:
 
 
 def ncu_traffic(family):
-    """DRAM bytes (read + write) of one launch of the family's kernel from the committed `ncu --set full`
-    capture (profiles/ncu_traffic_r1b.json; produced by profiles/call_ncu.sh on the same workload)."""
-    name = {"resblock_fwd": "k_resblock_fwd_tc", "conv": "k_conv_tc", "wgrad": "k_wgrad_tc_raw",
-            "vq_argmin": "k_vq_argmin_tc"}.get(family)
-    p = os.path.join(ROOT, "profiles", "ncu_traffic_r1b.json")
-    if name is None or not os.path.exists(p):
-        return None, None
-    k = json.load(open(p))["kernels"].get(name)
-    if not k:
-        return None, None
-    return k["dram_bytes_read"] + k["dram_bytes_write"], f"profiles/ncu_traffic_r1b.json: {k['kernel']}"
+    """DRAM bytes (read + write) of one launch of the family's kernel from the committed `ncu --set full` captures
+    (profiles/ncu_traffic_r2.json, produced by profiles/call_r2_17.sh + summarize_r2.py on the same workload; kernels that
+    capture did not reach fall back to round 1's profiles/ncu_traffic_r1b.json)."""
+    for fname, names in (("ncu_traffic_r2.json", {"resblock_fwd": "k_resblock_fwd_tc2", "conv": "k_conv_tc_dgrad",
+                                                  "wgrad": "k_wgrad_tc_raw", "vq_argmin": "k_vq_argmin_tf32"}),
+                         ("ncu_traffic_r1b.json", {"resblock_fwd": "k_resblock_fwd_tc", "conv": "k_conv_tc",
+                                                   "wgrad": "k_wgrad_tc_raw", "vq_argmin": "k_vq_argmin_tc"})):
+        p = os.path.join(ROOT, "profiles", fname)
+        name = names.get(family)
+        if name is None or not os.path.exists(p):
+            continue
+        k = json.load(open(p))["kernels"].get(name)
+        if k:
+            return k["dram_bytes_read"] + k["dram_bytes_write"], f"profiles/{fname}: {k['kernel']}"
+    return None, None
 
 
 def measured_peaks():
@@ -440,14 +444,19 @@ def run_b200(args, rank, local_rank, world):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "kernel": {"resblock_fwd": "k_resblock_fwd_tc (fused gated residual block forward)",
+                "kernel": {"resblock_fwd": "k_resblock_fwd_tc2 (fused gated residual block forward)",
                            "conv": "k_conv_tc (dgrad / plain conv family)",
-                           "wgrad": "k_wgrad_tc (weight-gradient family)"}[dom] if args.precision != "fp32" else dom,
+                           "wgrad": "k_wgrad_tc / k_wgrad_tc_raw (weight-gradient family)"}[dom] if args.precision != "fp32" else dom,
+                "selection": "the dense-contraction family with the largest share of the step; every family is listed under `families`",
+                "families": {k: {"ms_per_step": v["ms_per_step"], "tflops": v["tflops"],
+                                 "frac": (v["tflops"] / peak_tf) if (v["tflops"] and peak_tf) else None}
+                             for k, v in kern.items() if k != "vq_argmin"},
                 "bound": "tensor", "achieved": ach, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": ach / peak_tf if (peak_tf and ach) else None, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "all_dense_kernels": {"gflop_per_step": dense_gf, "ms_per_step": dense_ms,
-                                      "tflops": dense_gf / dense_ms if dense_ms else None},
+                                      "tflops": dense_gf / dense_ms if dense_ms else None,
+                                      "frac": (dense_gf / dense_ms / peak_tf) if (dense_ms and peak_tf) else None},
                 "peak_source": peaks_src + " bf16 sustained; kernel arithmetic: " + args.precision,
                 "share_of_step": rb.get("ms_per_step", 0.0) / (ms / args.steps) if rb else None,
             },

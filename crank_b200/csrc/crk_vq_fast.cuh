@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
     float* wn_s = Wb + 16 * CR4;               // [K]
     float* Xt = wn_s + K;                      // [16][129][4] raw fp32 X tile (A operand)
     float* xrows = Xt + 16 * CSX;              // [128][65] row-major copy (|x|^2, re-score, outputs)
+    float* wa_s = xrows + 128 * 65;            // [K] wn (1 + c)
+    float* wb_s = wa_s + K;                    // [K] wn (1 - c)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntiles = (p.F + 127) / 128;
 
@@ -141,32 +143,42 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
             for (int d = 0; d < 64; ++d) s = fmaf(xr[d], xr[d], s);      // same order as k_vq_argmin
             xn_s[r] = s;
         }
-        if (it == 0) ok &= tc::mbar_wait(&bar_w, 0);                      // wn_s / Wb visible to every thread
+        if (it == 0) {
+            ok &= tc::mbar_wait(&bar_w, 0);                               // wn_s / Wb visible to every thread
+            for (int k = threadIdx.x; k < K; k += 256) {
+                wa_s[k] = wn_s[k] * (1.f + CRK_VQ_TF32_RADIUS);
+                wb_s[k] = wn_s[k] * (1.f - CRK_VQ_TF32_RADIUS);
+            }
+        }
         ok &= tc::mbar_wait(&bar_acc, it & 1);
         tc::tc_fence_after();
         __syncthreads();
 
         // ---- epilogue: thread = (frame row r, code half) ----
+        // bounds with one FMA per code (the scan is instruction-bound: 512 codes x 128 frames per tile):
+        //   upper_k = dist~_k + m_k = fma(-2, dot_k, wn_k (1 + c)) + xn (1 + c),   lower_k = fma(-2, dot_k, wn_k (1 - c)) + xn (1 - c)
+        // with the per-code tables wa = wn (1 + c), wb = wn (1 - c) in shared memory (c carries 28 % of slack over the
+        // rigorous 2^-9: fp32 rounding of these expressions, ~1e-7 relative, cannot break the bounds)
         const int r = (warp & 3) * 32 + lane;
         const int half = warp >> 2;
         const int kbeg = half * (K >> 1), kend = kbeg + (K >> 1);
         const float xn = xn_s[r];
-        const float cx = CRK_VQ_TF32_RADIUS * xn;
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        float bu = INF;
+        float mub = INF;
         for (int k0 = kbeg; k0 < kend; k0 += 32) {
             float v[32];
             tc::tmem_ld32(tlane + k0, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float wn = wn_s[k0 + i];
-                const float dist = __fadd_rn(__fsub_rn(wn, 2.f * v[i]), xn);
-                bu = fminf(bu, dist + fmaf(CRK_VQ_TF32_RADIUS, wn, cx));
+            for (int i = 0; i < 32; i += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(wa_s + k0 + i);
+                mub = fminf(mub, fminf(fminf(fmaf(-2.f, v[i], a.x), fmaf(-2.f, v[i + 1], a.y)),
+                                       fminf(fmaf(-2.f, v[i + 2], a.z), fmaf(-2.f, v[i + 3], a.w))));
             }
         }
-        mbu_s[half][r] = bu;
+        mbu_s[half][r] = mub;
         __syncthreads();
-        bu = fminf(mbu_s[0][r], mbu_s[1][r]);
+        const float bu = fmaf(xn, 1.f + CRK_VQ_TF32_RADIUS, fminf(mbu_s[0][r], mbu_s[1][r]));     // best upper bound
+        const float thr = bu - xn * (1.f - CRK_VQ_TF32_RADIUS);
         int cand[CRK_VQ_MAXCAND];
         int ncand = 0;
 #pragma unroll
@@ -174,16 +186,22 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
         for (int k0 = kbeg; k0 < kend; k0 += 32) {
             float v[32];
             tc::tmem_ld32(tlane + k0, v);
+            uint32_t hit = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float wn = wn_s[k0 + i];
-                const float dist = __fadd_rn(__fsub_rn(wn, 2.f * v[i]), xn);
-                if (dist - fmaf(CRK_VQ_TF32_RADIUS, wn, cx) <= bu) {
+            for (int i = 0; i < 32; i += 4) {
+                const float4 bq = *reinterpret_cast<const float4*>(wb_s + k0 + i);
+                hit |= (fmaf(-2.f, v[i], bq.x) <= thr ? 1u : 0u) << i;
+                hit |= (fmaf(-2.f, v[i + 1], bq.y) <= thr ? 1u : 0u) << (i + 1);
+                hit |= (fmaf(-2.f, v[i + 2], bq.z) <= thr ? 1u : 0u) << (i + 2);
+                hit |= (fmaf(-2.f, v[i + 3], bq.w) <= thr ? 1u : 0u) << (i + 3);
+            }
+            while (hit) {                                   // rare: 1-2 candidates per frame over all 512 codes
+                const int i = __ffs(hit) - 1;
+                hit &= hit - 1;
 #pragma unroll
-                    for (int c = 0; c < CRK_VQ_MAXCAND; ++c)
-                        if (c == ncand) cand[c] = k0 + i;
-                    ++ncand;
-                }
+                for (int c = 0; c < CRK_VQ_MAXCAND; ++c)
+                    if (c == ncand) cand[c] = k0 + i;
+                ++ncand;
             }
         }
         // exact re-score, warp-converged: round c handles every lane's c-th candidate
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(512) k_vq_ema_fused(const float* __restrict__ 
 }
 
 inline size_t vq_fast_smem(int K) {
-    return (size_t)(16 * vq_op_rows(K) * 4 + K + 16 * 129 * 4 + 128 * 65) * sizeof(float);
+    return (size_t)(16 * vq_op_rows(K) * 4 + 3 * K + 16 * 129 * 4 + 128 * 65) * sizeof(float);
 }
 
 }  // namespace crk
