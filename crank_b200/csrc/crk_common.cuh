@@ -114,6 +114,11 @@ __host__ __device__ inline long long cdivl(long long a, long long b) { return (a
 
 // columns-per-thread needed for n output columns (TN = 32*cpt)
 __host__ __device__ inline int cpt_for(int n) { return n <= 32 ? 1 : n <= 64 ? 2 : n <= 96 ? 3 : 4; }
+// leading dimension of a packed matrix with n columns: 32*cpt up to 128 columns; wider (the first conv of a stack fed by
+// three concatenated 64-channel code streams, n_vq_stacks = 3: 192 input channels) rounded up to 32 -- such a matrix is
+// consumed in 128-column slices (ConvParams::ldw)
+__host__ __device__ inline int wide_ld(int n) { return n <= 128 ? 32 * cpt_for(n) : ((n + 31) / 32) * 32; }
+#define CRK_MAX_IN_CH 256
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     if (act == CRK_ACT_RELU) return v > 0.f ? v : 0.f;

@@ -16,6 +16,7 @@ namespace crk {
 struct ConvParams {
     const float* X; int ldx; int Cin; int CinPad;   // CinPad = round_up(Cin,4): smem row stride
     const float* W;      // [k][CinPad][TN]   zero padded, TN = 32*CPT
+    int ldw;             // 0: rows of W are TN apart; else the row stride of a wider matrix of which W is a TN-column slice
     const float* bias;   // [TN] or null
     float* Y; int ldy; int Cout;
     int B, T;
@@ -34,7 +35,7 @@ struct ConvParams {
 
 inline ConvParams conv_params_default() {
     ConvParams p;
-    p.X = nullptr; p.ldx = 0; p.Cin = 0; p.CinPad = 0; p.W = nullptr; p.bias = nullptr;
+    p.X = nullptr; p.ldx = 0; p.Cin = 0; p.CinPad = 0; p.W = nullptr; p.ldw = 0; p.bias = nullptr;
     p.Y = nullptr; p.ldy = 0; p.Cout = 0; p.B = 0; p.T = 0; p.k = 1; p.dil = 1; p.padl = 0;
     p.pro_act = CRK_ACT_NONE; p.pro_slope = 0.f; p.pro_scale = 1.f; p.xmul = nullptr; p.ldxmul = 0;
     p.epi_act = CRK_ACT_NONE; p.epi_slope = 0.f; p.mul_src = nullptr; p.ldmul = 0;
@@ -112,7 +113,14 @@ __global__ void __launch_bounds__(CRK_THREADS) k_conv(const ConvParams p) {
 
     for (int j = 0; j < p.k; ++j) {
         if (j > 0) __syncthreads();  // everyone done with the previous tap's weights
-        copy_to_smem(ws, p.W + (size_t)j * p.CinPad * TN, p.CinPad * TN);
+        if (p.ldw == 0 || p.ldw == TN) {
+            copy_to_smem(ws, p.W + (size_t)j * p.CinPad * TN, p.CinPad * TN);
+        } else {                                             // TN-column slice of a wider packed matrix
+            for (int idx = threadIdx.x; idx < p.CinPad * TN; idx += CRK_THREADS) {
+                const int r = idx / TN, cc = idx - r * TN;
+                ws[idx] = __ldg(p.W + ((size_t)j * p.CinPad + r) * p.ldw + cc);
+            }
+        }
         __syncthreads();
         tile_mac_rowA<CPT>(acc, xs + (ty * 8 + j * p.dil) * p.CinPad, p.CinPad, ws + tx * CPT, TN,
                            p.CinPad);

@@ -549,6 +549,23 @@ inline bool conv_pt_ok(const ConvTcParams& q, bool split);
 
 // precision-aware dispatch: tensor cores when enabled and the shape fits, else the fp32 kernel
 inline cudaError_t conv_dispatch(const ConvParams& p, int cpt, const float* wtc, int kpad, int npad, cudaStream_t s) {
+    if (p.Cout > 128) {
+        // more than 128 output columns: the dgrad of a stack's first conv when its input is wider than 128 channels
+        // (n_vq_stacks = 3: 192).  fp32 kernel over 128-column slices of the packed matrix (row stride wide_ld(Cout)).
+        const int ldw = wide_ld(p.Cout);
+        for (int n0 = 0; n0 < p.Cout; n0 += 128) {
+            ConvParams q = p;
+            q.W = p.W + n0; q.ldw = ldw; q.Cout = (p.Cout - n0) < 128 ? (p.Cout - n0) : 128;
+            if (p.bias) q.bias = p.bias + n0;
+            q.Y = p.Y + n0;
+            if (p.mul_src) q.mul_src = p.mul_src + n0;
+            if (p.R) q.R = p.R + n0;
+            if (p.dact_src) q.dact_src = p.dact_src + n0;
+            cudaError_t e = launch_conv(q, cpt_for(q.Cout), s);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     const int mode = precision_mode();
     if (mode != CRK_PREC_FP32 && !(tc_disable_mask() & 2)) {
         ConvTcParams q;

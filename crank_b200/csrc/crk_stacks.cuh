@@ -185,13 +185,13 @@ struct WavenetLayout {
 
 inline int wavenet_layout(const crk_wavenet_cfg* c, WavenetLayout* L) {
     if (!c || c->layers < 1 || c->layers > 32 || c->stacks < 1 || c->layers % c->stacks != 0) return CRK_ERR_ARG;
-    if (c->in_ch < 1 || c->in_ch > 128 || c->out_ch < 1 || c->out_ch > 128 || c->aux_ch > 128) return CRK_ERR_ARG;
+    if (c->in_ch < 1 || c->in_ch > CRK_MAX_IN_CH || c->out_ch < 1 || c->out_ch > 128 || c->aux_ch > 128) return CRK_ERR_ARG;
     if (c->kernel_size < 1 || c->kernel_size > 9) return CRK_ERR_ARG;
     if (!c->causal && (c->kernel_size % 2) == 0) return CRK_ERR_ARG;
     const int n_convs = 1 + c->layers * (c->aux_ch > 0 ? 4 : 3) + 2;
     if (n_convs > CRK_MAX_CONVS) return CRK_ERR_UNSUPPORTED;
     LayoutBuilder b;
-    L->first = b.add(64, c->in_ch, 1, true, 0, 64, 64, 32 * cpt_for(c->in_ch));
+    L->first = b.add(64, c->in_ch, 1, true, 0, 64, 64, wide_ld(c->in_ch));
     for (int l = 0; l < c->layers; ++l) {
         L->conv[l] = b.add(128, 64, c->kernel_size, true, 1, 128, 128, 64);
         L->aux[l] = c->aux_ch > 0 ? b.add(128, c->aux_ch, 1, false, 1, 128, 128, 32 * cpt_for(c->aux_ch)) : -1;
@@ -472,7 +472,7 @@ inline int convstack_layout(const crk_convstack_cfg* c, ConvstackLayout* L) {
     if (!c || c->layers < 1 || c->layers > 32 || c->kernel_size < 1 || c->kernel_size > 9 ||
         (c->kernel_size % 2) == 0 || c->dilation_factor < 1)
         return CRK_ERR_ARG;
-    if (c->in_ch < 1 || c->in_ch > 128 || c->out_ch < 1 || c->out_ch > 128 || c->conv_ch < 1 || c->conv_ch > 128)
+    if (c->in_ch < 1 || c->in_ch > CRK_MAX_IN_CH || c->out_ch < 1 || c->out_ch > 128 || c->conv_ch < 1 || c->conv_ch > 128)
         return CRK_ERR_ARG;
     LayoutBuilder b;
     for (int i = 0; i < c->layers; ++i) {
@@ -493,7 +493,7 @@ inline int convstack_layout(const crk_convstack_cfg* c, ConvstackLayout* L) {
         const int cout = last ? c->out_ch : c->conv_ch;
         if ((c->kernel_size - 1) * dil > 64) return CRK_ERR_UNSUPPORTED;
         L->cin[i] = cin; L->cout[i] = cout; L->dil[i] = dil;
-        b.add(cout, cin, c->kernel_size, true, 0, 32 * cpt_for(cout), round_up(cout, 4), 32 * cpt_for(cin));
+        b.add(cout, cin, c->kernel_size, true, 0, 32 * cpt_for(cout), round_up(cout, 4), wide_ld(cin));
     }
     L->tab = b.tab; L->theta = b.theta; L->weff = b.weff;
     return CRK_OK;

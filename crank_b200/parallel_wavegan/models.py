@@ -156,11 +156,10 @@ class _WavenetBase(_PackedConvNet):
     def _build(self, in_channels, out_channels, aux_channels, layers, stacks, kernel_size,
                use_causal_conv, first_act, head_act, slope, dropout, first_name, use_weight_norm):
         assert layers % stacks == 0
-        if max(int(in_channels), int(out_channels), int(aux_channels)) > 128:
+        if int(in_channels) > 256 or max(int(out_channels), int(aux_channels)) > 128:
             raise NotImplementedError(
                 f"WaveNet stack with {in_channels} input / {out_channels} output / {aux_channels} aux channels: the "
-                "sm_100a kernels take at most 128 channels per operand (every shipped recipe fits; n_vq_stacks=3 "
-                "needs a 192-channel decoder input)")
+                "sm_100a kernels take at most 256 input and 128 output / aux channels (n_vq_stacks = 3 needs 192 inputs)")
         self.cfg = L.WavenetCfg(
             in_ch=in_channels, out_ch=out_channels, aux_ch=max(int(aux_channels), 0), layers=layers,
             stacks=stacks, kernel_size=kernel_size, causal=int(bool(use_causal_conv)),

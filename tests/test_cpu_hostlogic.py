@@ -77,6 +77,7 @@ def test_product_train_steps_match_oracle_with_emulated_ops(kind):
     ("lsgan", dict(causal=True, causal_size=4)),
     ("cyclegan", dict(causal=True, causal_size=4)),
     ("vqvae", dict(n_vq_stacks=1)),
+    ("cyclegan", dict(n_vq_stacks=3)),
     ("lsgan", dict(use_spkr_embedding=False)),
     ("cyclegan", dict(encoder_f0=True)),
     ("lsgan", dict(ema_flag=False)),
@@ -91,15 +92,18 @@ def test_product_host_logic_on_config_variants(kind, overrides):
     _run(kind, overrides, T=176 if overrides.get("causal") else 96, steps=1 if overrides.get("causal") else 2)
 
 
-def test_three_vq_stacks_fail_loudly():
-    """n_vq_stacks = 3 makes the bottom decoder's input 192 channels wide; the kernels take at most 128, and the
-    product says so at construction instead of computing something else."""
-    from crank_b200.conf import vcc2020_conf
-    from crank_b200.net.trainer import get_model
+def test_too_wide_stacks_fail_loudly():
+    """The kernels take at most 256 input channels (n_vq_stacks = 3 needs 192: built, see the variant above and
+    tests/test_gpu_trainstep.py) and 128 output / aux channels; anything wider says so at construction."""
+    from crank_b200.parallel_wavegan.models import ParallelWaveGANGenerator
 
     with emulated_ops():
-        with pytest.raises(NotImplementedError, match="128"):
-            get_model(vcc2020_conf(trainer_type="vqvae", n_vq_stacks=3), S, device="cpu")
+        with pytest.raises(NotImplementedError, match="at most 256 input"):
+            ParallelWaveGANGenerator(in_channels=320, out_channels=80, kernel_size=5, layers=8, stacks=4, aux_channels=0,
+                                     upsample_conditional_features=False)
+        with pytest.raises(NotImplementedError, match="at most 256 input"):
+            ParallelWaveGANGenerator(in_channels=64, out_channels=80, kernel_size=5, layers=8, stacks=4, aux_channels=192,
+                                     upsample_conditional_features=False)
 
 
 def test_emulation_is_test_only_and_restored():

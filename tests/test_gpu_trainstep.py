@@ -29,11 +29,14 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_train_golden.npz")
 S, B, T = 14, 2, 96
 
 
+_CONF_OVERRIDES = {}
+
+
 def _conf(kind):
     from crank_b200.conf import vcc2020_conf
 
     return vcc2020_conf(trainer_type=kind, n_steps_gan_start=-1, n_steps_cycle_start=-1,
-                        discriminator_dropout=0.0)
+                        discriminator_dropout=0.0, **_CONF_OVERRIDES)
 
 
 class _W:
@@ -255,3 +258,33 @@ def test_no_grad_forward_and_skipped_final_decoder_are_invisible():
             assert torch.equal(Ga.quantizers[n].ema_w, other.quantizers[n].ema_w)
             assert torch.equal(Ga.quantizers[n].ema_size, other.quantizers[n].ema_size)
             assert torch.equal(Ga.quantizers[n].embedding.weight, other.quantizers[n].embedding.weight)
+
+
+@pytest.mark.parametrize("kind", ["vqvae", "cyclegan"])
+def test_three_vq_stacks_train_step_matches_oracle(kind):
+    """n_vq_stacks = 3 (egs/vaevc/template/conf/default.yml:98-103; vqvae2.py:211-283): the bottom decoder and the speaker-
+    adversarial classifier read 192 channels (three concatenated 64-channel code streams).  Their first convs run
+    as 128-column slices of the packed matrices (crk_conv_tc.cuh conv_dispatch / ConvParams::ldw); losses of two train steps
+    against the oracle (which is bit-identical to the live reference on this variant: tests/test_cpu_oracle.py)."""
+    from crank_b200.synthetic import clone_batch, make_batch, to_device
+
+    _CONF_OVERRIDES["n_vq_stacks"] = 3
+    try:
+        conf, om, pm, O, P = _build_pair(kind)
+    finally:
+        _CONF_OVERRIDES.clear()
+    assert len(pm["G"].quantizers) == 3
+    batch = make_batch(B, T, S, seed=0, ragged=True)
+    for it in range(2):
+        random.seed(100 + it)
+        ov = O.train(clone_batch(batch), "train")
+        random.seed(100 + it)
+        pv = P.train(to_device(clone_batch(batch), "cuda"), "train")
+        assert set(ov) == set(pv), set(ov) ^ set(pv)
+        worst = 0.0
+        for k in sorted(ov):
+            ref = ov[k]
+            err = abs(pv[k] - ref) / max(abs(ref), 1e-12) if ref != 0 else abs(pv[k])
+            worst = max(worst, err)
+            assert err <= 1e-4, f"{kind} n_vq_stacks=3 step {it} loss {k}: product {pv[k]} vs oracle {ref} (rel {err:.2e})"
+        print(f"{kind} n_vq_stacks=3 step {it}: {len(ov)} loss keys, worst rel err {worst:.2e}")
