@@ -517,6 +517,34 @@ int crk_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
     return CRK_OK;
 }
 
+int crk_radam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, int step_count, void* stream) {
+    if (!p || !g || !m || !v || n < 1 || step_count < 1) return CRK_ERR_ARG;
+    // python-double scalars of torch_optimizer.RAdam.step
+    const double b1 = beta1, b2 = beta2, st = step_count;
+    const double beta2_t = pow(b2, st);
+    const double n_sma_max = 2.0 / (1.0 - b2) - 1.0;
+    const double n_sma = n_sma_max - 2.0 * st * beta2_t / (1.0 - beta2_t);
+    const int rect = n_sma >= 5.0;
+    double step_size = (double)lr / (1.0 - pow(b1, st));
+    if (rect)
+        step_size = (double)lr * sqrt((1.0 - beta2_t) * (n_sma - 4.0) / (n_sma_max - 4.0) * (n_sma - 2.0) / n_sma * n_sma_max / (n_sma_max - 2.0)) /
+                    (1.0 - pow(b1, st));
+    k_radam<<<(unsigned)cdivl(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, beta1, beta2, eps, (float)step_size, rect);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+
+int crk_lamb_step(float* p, const float* g, float* m, float* v, float* upd, const long long* seg_off, const long long* seg_len,
+                  int nseg, float* trust, float lr, float beta1, float beta2, float eps, void* stream) {
+    if (!p || !g || !m || !v || !upd || !seg_off || !seg_len || !trust || nseg < 1) return CRK_ERR_ARG;
+    k_lamb_moments<<<nseg, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, upd, seg_off, seg_len, trust, beta1, beta2, eps);
+    API_TRY(launch_check());
+    k_lamb_apply<<<nseg, 256, 0, (cudaStream_t)stream>>>(p, upd, seg_off, seg_len, trust, lr);
+    API_TRY(launch_check());
+    return CRK_OK;
+}
+
 int crk_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                       float beta2, float eps, long long* step_dev, void* stream) {
     if (!p || !g || !m || !v || !step_dev || n < 1) return CRK_ERR_ARG;

@@ -435,4 +435,60 @@ __global__ void k_adam_dev(float* __restrict__ p, const float* __restrict__ g, f
     p[i] = p[i] - step_size * (mi / denom);
 }
 
+// ---- RAdam (torch_optimizer.RAdam as constructed at crank/net/trainer/utils.py:44-45: lr, betas (0.9, 0.999), eps 1e-8,
+// no weight decay).  The rectification term and bias corrections are host scalars (python floats in the original):
+//   rect != 0:  p -= step_size * m / (sqrt(v) + eps)        rect == 0 (variance not yet tractable, N_sma < 5):  p -= step_size * m
+__global__ void k_radam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                        long long n, float beta1, float beta2, float eps, float step_size, int rect) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i];
+    const float vi = __fadd_rn(__fmul_rn(v[i], beta2), __fmul_rn(__fmul_rn(1.f - beta2, gi), gi));   // mul_(b2).addcmul_(g, g, 1-b2)
+    const float mi = __fadd_rn(__fmul_rn(m[i], beta1), __fmul_rn(1.f - beta1, gi));                    // mul_(b1).add_(g, 1-b1)
+    m[i] = mi; v[i] = vi;
+    p[i] = rect ? p[i] - step_size * (mi / (sqrtf(vi) + eps)) : p[i] - step_size * mi;
+}
+
+// ---- LAMB (pytorch_lamb.Lamb as constructed at crank/net/trainer/utils.py:46-47: lr, betas (0.9, 0.999), eps 1e-6, no
+// weight decay, no bias correction).  The trust ratio is per PARAMETER TENSOR of the reference (weight_g / weight_v / bias
+// of every conv): one segment of the flat parameter pack each.  Pass 1 (one CTA per segment): moments, the Adam direction
+// u = m / (sqrt(v) + eps) into `upd`, ||p|| (clamped to [0, 10]) and ||u|| -> trust[seg];  pass 2: p -= lr * trust * u.
+__global__ void __launch_bounds__(256) k_lamb_moments(const float* __restrict__ p, const float* __restrict__ g,
+                                                      float* __restrict__ m, float* __restrict__ v, float* __restrict__ upd,
+                                                      const long long* __restrict__ seg_off, const long long* __restrict__ seg_len,
+                                                      float* __restrict__ trust, float beta1, float beta2, float eps) {
+    __shared__ double red[2][256];
+    const long long o = seg_off[blockIdx.x], n = seg_len[blockIdx.x];
+    double sp = 0.0, su = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+        const float gi = g[o + i];
+        const float mi = __fadd_rn(__fmul_rn(m[o + i], beta1), __fmul_rn(1.f - beta1, gi));
+        const float vi = __fadd_rn(__fmul_rn(v[o + i], beta2), __fmul_rn(__fmul_rn(1.f - beta2, gi), gi));
+        m[o + i] = mi; v[o + i] = vi;
+        const float u = mi / (sqrtf(vi) + eps);
+        upd[o + i] = u;
+        const float pi = p[o + i];
+        sp += (double)pi * pi;
+        su += (double)u * u;
+    }
+    red[0][threadIdx.x] = sp; red[1][threadIdx.x] = su;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { red[0][threadIdx.x] += red[0][threadIdx.x + s]; red[1][threadIdx.x] += red[1][threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float wn = fminf(fmaxf((float)sqrt(red[0][0]), 0.f), 10.f);
+        const float an = (float)sqrt(red[1][0]);
+        trust[blockIdx.x] = (wn == 0.f || an == 0.f) ? 1.f : wn / an;
+    }
+}
+__global__ void __launch_bounds__(256) k_lamb_apply(float* __restrict__ p, const float* __restrict__ upd,
+                                                    const long long* __restrict__ seg_off, const long long* __restrict__ seg_len,
+                                                    const float* __restrict__ trust, float lr) {
+    const long long o = seg_off[blockIdx.x], n = seg_len[blockIdx.x];
+    const float s = lr * trust[blockIdx.x];
+    for (long long i = threadIdx.x; i < n; i += 256) p[o + i] = p[o + i] - s * upd[o + i];
+}
+
 }  // namespace crk

@@ -102,6 +102,8 @@ SIGNATURES = {
     "crk_ce_fwd": (i32, [vp, i32, vp, i64, i32, i64, vp, vp, vp]),
     "crk_ce_bwd": (i32, [vp, i32, vp, i64, i32, i64, vp, vp, vp, i32, vp]),
     "crk_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
+    "crk_radam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
+    "crk_lamb_step": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, f32, f32, f32, f32, vp]),
     "crk_adam_step_dev": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]),
     "crk_logmel_ws_floats": (i64, [i32, i32, i32]),
     "crk_logmel_fwd": (i32, [vp, i32, i64, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),

@@ -11,7 +11,7 @@ from ...parallel_wavegan.models import (
     ParallelWaveGANDiscriminator,
     ResidualParallelWaveGANDiscriminator,
 )
-from .optim import FusedAdam
+from .optim import FusedAdam, FusedLamb, FusedRAdam
 
 
 def get_criterion(conf, device="cuda"):
@@ -31,9 +31,10 @@ def get_optimizer(conf, model):
     for m in ["G", "D", "C", "SPKRADV"]:
         if m in model:
             kind = conf["optim"][m]["type"]
-            if kind != "adam":
-                raise ValueError(f"Invalid optimizer type {kind!r}: only 'adam' (the recipes' default) is built")
-            optimizer[m] = FusedAdam(model[m].parameters(), lr=conf["optim"][m]["lr"])
+            table = {"adam": FusedAdam, "radam": FusedRAdam, "lamb": FusedLamb}     # crank/net/trainer/utils.py:41-49
+            if kind not in table:
+                raise ValueError("Invalid optimizer type")
+            optimizer[m] = table[kind](model[m].parameters(), lr=conf["optim"][m]["lr"])
     return optimizer
 
 

@@ -397,6 +397,20 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step_count):
            C.c_float(beta1), C.c_float(beta2), C.c_float(eps), int(step_count))
 
 
+def radam_step(p, g, m, v, lr, beta1, beta2, eps, step_count):
+    L.require_cuda(p, g, m, v)
+    L.call("crk_radam_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), C.c_float(lr), C.c_float(beta1),
+           C.c_float(beta2), C.c_float(eps), int(step_count))
+
+
+def lamb_step(p, g, m, v, upd, seg_off, seg_len, trust, lr, beta1, beta2, eps):
+    L.require_cuda(p, g, m, v, upd, seg_off, seg_len, trust)
+    if not p.is_contiguous():
+        raise ValueError("lamb_step needs a contiguous parameter")
+    L.call("crk_lamb_step", L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(upd), L.ptr(seg_off), L.ptr(seg_len),
+           int(seg_off.numel()), L.ptr(trust), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps))
+
+
 def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, step_dev):
     """Adam with the step counter in device memory (int64 tensor of one element, incremented by the call)."""
     L.require_cuda(p, g, m, v, step_dev)

@@ -42,6 +42,15 @@ class _PackedConvNet(torch.nn.Module):
         self._use_weight_norm = use_weight_norm
         self._weight_norm_removed = not use_weight_norm
         self.theta = torch.nn.Parameter(torch.zeros(int(theta_floats)))
+        # the reference's parameter tensors inside the flat pack (weight_g / weight_v / bias of every conv): per-tensor
+        # optimizers (LAMB's trust ratio) work on these segments
+        segs = []
+        for d in descs:
+            segs.append((int(d.g_off), int(d.cout)))
+            segs.append((int(d.v_off), int(d.cout * d.cin * d.k)))
+            if d.b_off >= 0:
+                segs.append((int(d.b_off), int(d.cout)))
+        self.theta._crk_segments = segs
         self._weff = None
         self._weff_key = None
         self.reset_parameters()

@@ -258,6 +258,15 @@ int crk_ce_bwd(const float* logits, int ldl, const long long* labels, long long 
  * state: m, v same size as p; step_count is the 1-based step number AFTER this update. */
 int crk_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                   float beta2, float eps, int step_count, void* stream);
+/* The other two optimizers crank/net/trainer/utils.py:40-58 can build.  crk_radam_step: torch_optimizer.RAdam (lr, betas
+ * (0.9, 0.999), eps 1e-8; rectified update once the variance is tractable, plain momentum step before).  crk_lamb_step:
+ * pytorch_lamb.Lamb (eps 1e-6, no bias correction, weight norm clamped to [0, 10]); the trust ratio is per parameter
+ * tensor of the reference, i.e. per segment [seg_off[i], seg_off[i] + seg_len[i]) of the flat pack (device arrays of
+ * nseg int64); upd (n floats) and trust (nseg floats) are scratch. */
+int crk_radam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, int step_count, void* stream);
+int crk_lamb_step(float* p, const float* g, float* m, float* v, float* upd, const long long* seg_off, const long long* seg_len,
+                  int nseg, float* trust, float lr, float beta1, float beta2, float eps, void* stream);
 /* Same update with the step count in DEVICE memory (*step_dev is incremented first, then used for the bias
  * corrections): no per-step host value in the launch arguments, so the call can be captured in a CUDA graph and
  * replayed (crank_b200/net/graph.py). */

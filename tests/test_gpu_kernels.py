@@ -571,3 +571,38 @@ def test_learnable_stft_windows_train(window):
         e = (got.cpu().double() - want).abs().max() / want.abs().max()
         print(f"learnable window {window}: forward {e_o:.2e}, parameter gradient rel err {e:.2e}")
         assert e <= 2e-4, e
+
+
+@pytest.mark.parametrize("kind", ["radam", "lamb"])
+def test_radam_and_lamb_match_the_restated_reference_optimizers(kind):
+    """get_optimizer's "radam" / "lamb" (crank/net/trainer/utils.py:44-47) on a weight-normed conv stack: 8 steps (RAdam:
+    5 momentum-only steps, then rectified ones) against oracle/optim_port.py on the oracle's per-tensor parameters --
+    LAMB's trust ratios must be those of the reference's weight_g / weight_v / bias tensors, not of the flat pack."""
+    from crank_b200.net.trainer.optim import FusedLamb, FusedRAdam
+    from crank_b200.parallel_wavegan.models import ParallelWaveGANDiscriminator as PD
+    from oracle import optim_port as oo
+    from oracle.pwg import ParallelWaveGANDiscriminator as OD
+
+    torch.manual_seed(4)
+    kw = dict(in_channels=80, out_channels=14, kernel_size=5, layers=4, conv_channels=64)
+    o = OD(**kw)
+    p = PD(**kw)
+    p.load_state_dict(o.state_dict())
+    p = p.to(_dev())
+    oopt = (oo.RAdam if kind == "radam" else oo.Lamb)(o.parameters(), lr=1e-2)
+    popt = (FusedRAdam if kind == "radam" else FusedLamb)(p.parameters(), lr=1e-2)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 80, 200, generator=g)
+    for it in range(8):
+        tgt = torch.randn(2, 14, 200, generator=g)
+        oopt.zero_grad(); popt.zero_grad()
+        (o(x) - tgt).square().mean().backward()
+        (p(x.to(_dev())) - tgt.to(_dev())).square().mean().backward()
+        oopt.step(); popt.step()
+    osd, psd = o.state_dict(), p.state_dict()
+    worst = 0.0
+    for k, v in osd.items():
+        e = (psd[k].cpu() - v).abs().max().item() / max(v.abs().max().item(), 1e-12)
+        worst = max(worst, e)
+    print(f"{kind}: 8 steps, worst parameter rel err {worst:.2e}")
+    assert worst <= 2e-4, worst
