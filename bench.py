@@ -36,8 +36,8 @@ T_FRAMES = 500
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50, help="timed steps (SURVEY.md section 8d: >= 50 after >= 10 warm-up steps)")
+    ap.add_argument("--warmup", type=int, default=10, help="untimed warm-up steps (at least 3 are always run; the line reports the number used)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=T_FRAMES)

@@ -208,10 +208,11 @@ __host__ __device__ constexpr int chunk_stride_bytes(int rows) { return chunk_ro
 // flip ReLU derivatives of near-zero pre-activations in backward ~10x more often than the fp32 kernels do
 // (profiles/diag_r2c.py).  The tensor core truncates its fp32 operands to tf32 (profiles/hwprobe T4), which is exact
 // for values that are already tf32-representable.
+// (cvt.rna.tf32.f32 compiles to FSETP |x| < inf + predicated IADD + LOP3; the same rounding -- nearest, ties away from
+// zero, on the magnitude bits -- is an add of half a tf32 ulp and a mask: inf stays inf, NaN stays NaN, and a value that
+// rounds past the largest finite tf32 becomes inf exactly as cvt does.  One instruction less on every operand element.)
 __device__ __forceinline__ float rn_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = rn_tf32(x);

@@ -281,6 +281,8 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     if (warp == 1) tc::tmem_dealloc<512>(tmem);
 }
 
+__host__ __device__ inline size_t wgrad_raw_half(int Npad, int k, int dil) { return (size_t)(CRK_WG_TF + (k - 1) * dil) * (Npad + 4); }
+
 // ---- raw-tile variant (k > 1) --------------------------------------------------------------------
 // The k tap tiles of one 64-frame tile are the SAME (64 + halo) input rows shifted by j*dil frames.
 // k_wgrad_tc fetches each of them from global memory (k latency-bound round trips per tile, one per
@@ -327,8 +329,11 @@ __device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, co
     }
 }
 
-template <int NR, int C4L>
-__device__ __forceinline__ void wg_store_raw(const WgRegs<NR>& R, float* xraw, int stride, int c4n, int rows,
+// SPLIT: the hi / lo parts are produced HERE, once per input element, into two raw copies (xraw | xraw_lo): round 1 re-split
+// the same element for every one of the k taps that read it (ncu, round 2: the split arithmetic + its stores were ~40 % of
+// the kernel's issue slots for k = 5)
+template <bool SPLIT, int NR, int C4L>
+__device__ __forceinline__ void wg_store_raw(const WgRegs<NR>& R, float* xraw, float* xraw_lo, int stride, int c4n, int rows,
                                              int pro_act, float pro_slope, float pro_scale) {
     const int total = rows * c4n;
 #pragma unroll
@@ -341,14 +346,22 @@ __device__ __forceinline__ void wg_store_raw(const WgRegs<NR>& R, float* xraw, i
         x.y = apply_act(R.v[u].y * pro_scale, pro_act, pro_slope) * R.m[u].y;
         x.z = apply_act(R.v[u].z * pro_scale, pro_act, pro_slope) * R.m[u].z;
         x.w = apply_act(R.v[u].w * pro_scale, pro_act, pro_slope) * R.m[u].w;
-        *reinterpret_cast<float4*>(xraw + r * stride + c4 * 4) = x;
+        if (SPLIT) {
+            float4 h, l;
+            tc::split_tf32(x.x, h.x, l.x); tc::split_tf32(x.y, h.y, l.y);
+            tc::split_tf32(x.z, h.z, l.z); tc::split_tf32(x.w, h.w, l.w);
+            *reinterpret_cast<float4*>(xraw + r * stride + c4 * 4) = h;
+            *reinterpret_cast<float4*>(xraw_lo + r * stride + c4 * 4) = l;
+        } else {
+            *reinterpret_cast<float4*>(xraw + r * stride + c4 * 4) = x;
+        }
     }
 }
 
 // transposed hi/lo operand tile of one tap from the raw rows: elem(frame f, channel c) = xraw[f + shift][c]
 template <bool SPLIT, int NX>
-__device__ __forceinline__ void wg_transpose_raw(const float* xraw, int stride, float* hi, float* lo, int cs_floats,
-                                                 int nrows_pad, int shift) {
+__device__ __forceinline__ void wg_transpose_raw(const float* xraw, const float* xraw_lo, int stride, float* hi, float* lo,
+                                                 int cs_floats, int nrows_pad, int shift) {
     const int total = CRK_WG_TF * (nrows_pad >> 2);
 #pragma unroll
     for (int u = 0; u < NX; ++u) {
@@ -357,17 +370,10 @@ __device__ __forceinline__ void wg_transpose_raw(const float* xraw, int stride, 
         const int c4 = idx >> 6, f = idx & 63;
         const float4 v = *reinterpret_cast<const float4*>(xraw + (f + shift) * stride + c4 * 4);
         const int off = (f >> 2) * cs_floats + c4 * 16 + (f & 3);
-        const float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (SPLIT) {
-                float h, l;
-                tc::split_tf32(x[e], h, l);
-                hi[off + e * 4] = h;
-                lo[off + e * 4] = l;
-            } else {
-                hi[off + e * 4] = x[e];
-            }
+        hi[off] = v.x; hi[off + 4] = v.y; hi[off + 8] = v.z; hi[off + 12] = v.w;
+        if (SPLIT) {
+            const float4 w = *reinterpret_cast<const float4*>(xraw_lo + (f + shift) * stride + c4 * 4);
+            lo[off] = w.x; lo[off + 4] = w.y; lo[off + 8] = w.z; lo[off + 12] = w.w;
         }
     }
 }
@@ -399,6 +405,7 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     const int slot_floats = (SPLIT ? 2 : 1) * xhalf;
     const int NS = q.nslot;
     float* xraw = ring + NS * slot_floats;
+    float* xraw_lo = xraw + wgrad_raw_half(q.Npad, p.k, p.dil);        // (SPLIT only)
     const int rstride = q.Npad + 4;
     const int c4n = q.Npad >> 2;
     const int rows_raw = CRK_WG_TF + (p.k - 1) * p.dil;
@@ -455,7 +462,7 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
                     bsum[u].x += RG.v[u].x; bsum[u].y += RG.v[u].y; bsum[u].z += RG.v[u].z; bsum[u].w += RG.v[u].w;
                 }
             }
-            wg_store_raw<NR, C4L>(RX, xraw, rstride, c4n, rows_raw, p.pro_act, p.pro_slope, p.pro_scale);
+            wg_store_raw<SPLIT, NR, C4L>(RX, xraw, xraw_lo, rstride, c4n, rows_raw, p.pro_act, p.pro_slope, p.pro_scale);
             if (tile + 1 < tile_end) load_tile(tile + 1);  // a whole tile (k tap iterations) of latency cover
             asm volatile("bar.sync 1, 256;" ::: "memory");  // workers only: xraw complete
             if (tile == tile_beg) dbg_stamp(q.dbg, 2);
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
                 const int sl = step % NS;
                 // the MMAs of step - NS (this tile; earlier tiles are covered by bar_tile) read this slot
                 if (j >= NS) ok &= tc::mbar_wait(&bar_slot[sl], ((step - NS) / NS) & 1);
-                wg_transpose_raw<SPLIT, NX>(xraw, rstride, slot_hi(sl), slot_lo(sl), csx, q.Npad, j * p.dil);
+                wg_transpose_raw<SPLIT, NX>(xraw, xraw_lo, rstride, slot_hi(sl), slot_lo(sl), csx, q.Npad, j * p.dil);
                 tc::fence_proxy_async_smem();               // generic-proxy writes (G^T, slot) -> async proxy
                 tc::mbar_arrive(&bar_full[sl]);
             }
@@ -549,11 +556,11 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
 }
 
 // raw-tile variant: shared-memory plan and applicability
-inline size_t wgrad_raw_floats(int Npad, int k, int dil) { return (size_t)(CRK_WG_TF + (k - 1) * dil) * (Npad + 4); }
+inline size_t wgrad_raw_floats(int Npad, int k, int dil, bool split) { return (split ? 2 : 1) * wgrad_raw_half(Npad, k, dil); }
 inline int wgrad_raw_nslot(int Npad, int k, int dil, bool split) {
     const size_t g = (size_t)16 * 129 * 4 * (split ? 2 : 1), x = (size_t)16 * tc::chunk_rows(Npad) * 4 * (split ? 2 : 1);
-    const size_t budget = 200 * 1024 / sizeof(float);
-    const size_t fixed = g + wgrad_raw_floats(Npad, k, dil);
+    const size_t budget = 215 * 1024 / sizeof(float);
+    const size_t fixed = g + wgrad_raw_floats(Npad, k, dil, split);
     if (fixed + 2 * x > budget) return 0;
     const size_t n = (budget - fixed) / x;
     return n >= 4 ? 4 : (int)n;
@@ -578,7 +585,7 @@ inline cudaError_t launch_wgrad_tc_raw_nx(const WgradTcParams& q, int nchunk, cu
         attr_set = true;
     }
     const size_t g = (size_t)16 * 129 * 4 * (SPLIT ? 2 : 1), x = (size_t)16 * tc::chunk_rows(q.Npad) * 4 * (SPLIT ? 2 : 1);
-    const size_t smem = (g + q.nslot * x + wgrad_raw_floats(q.Npad, q.p.k, q.p.dil)) * sizeof(float);
+    const size_t smem = (g + q.nslot * x + wgrad_raw_floats(q.Npad, q.p.k, q.p.dil, SPLIT)) * sizeof(float);
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
     cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L>, dim3(nchunk), dim3(288), smem, s, q);
     if (le != cudaSuccess) return le;
