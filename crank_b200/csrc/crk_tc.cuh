@@ -82,6 +82,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// TMA 1-D bulk copy shared -> global (one thread issues; 16 B aligned, size % 16 == 0), then wait until the whole group has
+// completed.  Round 2 experiment (opt-in, crk_debug_opt_enable 4): the wgrad kernels' partial-sum epilogue stores 128 B per
+// warp instruction from the thread-per-row tensor-memory layout at ~5.4 B/clk per SM (30 K of 97 K cycles for k = 5); staging
+// the block in shared memory and handing it to the copy engine was measured SLOWER (8.0 vs 7.75 ms per step).
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

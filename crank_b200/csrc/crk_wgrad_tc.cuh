@@ -20,6 +20,8 @@ namespace crk {
 #define CRK_WG_TF 64   // frames per tile (UMMA K = 64 per tile and tap)
 
 struct WgradTcParams {
+    int gbuf;          // k_wgrad_tc: number of G^T buffers (1 or 2)
+    long long stage_floats;   // dynamic shared memory of the launch in floats (the epilogue stages the partial block there)
     WgradParams p;     // same contract as the fp32 kernel (p.part = [nchunk][k][Rows][TN])
     int TN;            // packed columns of G / dW (32*cpt)
     int Npad;          // UMMA N = round_up(Cin, 16)
@@ -112,16 +114,20 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
     __shared__ uint64_t bar_slot[4];
-    __shared__ uint64_t bar_tile;
+    __shared__ uint64_t bar_tile[2];                       // all MMAs of the tile in G^T buffer b have completed
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
 
     constexpr int KCH = CRK_WG_TF / 4;                     // 16 frame chunks per tile
     constexpr int CSG = 129 * 4;                           // G^T: 128 rows -> 129
     const int csx = tc::chunk_rows(q.Npad) * 4;
+    // G^T buffers: q.gbuf = 2 (round 2, when shared memory allows): the tile n+1 stores run under the MMAs of tile n -- with
+    // one buffer every tile waited for the previous tile's MMAs before its first store (k = 1: the whole tile was serial)
+    const int NGB = q.gbuf;
+    const int gstride = (SPLIT ? 2 : 1) * KCH * CSG;       // floats per G^T buffer (hi | lo)
     float* Gh = smem;
     float* Gl = Gh + KCH * CSG;
-    float* ring = Gl + (SPLIT ? KCH * CSG : 0);
+    float* ring = Gh + NGB * gstride;
     const int xhalf = KCH * csx;
     const int slot_floats = (SPLIT ? 2 : 1) * xhalf;
     const int NS = q.nslot;
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) tc::mbar_init(&bar_slot[i], 1);
-        tc::mbar_init(&bar_tile, 1);
+        tc::mbar_init(&bar_tile[0], 1); tc::mbar_init(&bar_tile[1], 1);
         tc::fence_mbar_init();
         timeout_s = 0;
     }
@@ -181,11 +187,13 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     if (tile_beg < tile_end) { load_g(tile_beg); load_x(tile_beg, 0); }
     for (int tile = tile_beg; tile < tile_end; ++tile) {
         if (tile == tile_beg) dbg_stamp(q.dbg, 0);
-        // G and first-tap X of this tile are already in registers (prefetched); wait for the previous
-        // tile's MMAs (they read the G^T buffer and the ring slot we are about to overwrite)
-        if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
+        // G and first-tap X of this tile are already in registers (prefetched); wait for the MMAs of the tile that used this
+        // G^T buffer last, and for the MMAs that read the ring slot we are about to overwrite
+        const int gb = ntile_done % NGB, guse = ntile_done / NGB;
+        if (guse > 0) { ok &= tc::mbar_wait(&bar_tile[gb], (guse - 1) & 1); tc::tc_fence_after(); }
+        if (step >= NS) { ok &= tc::mbar_wait(&bar_slot[step % NS], ((step - NS) / NS) & 1); tc::tc_fence_after(); }
         if (tile == tile_beg) dbg_stamp(q.dbg, 1);
-        wg_store<SPLIT, 8>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
+        wg_store<SPLIT, 8>(RG, Gh + gb * gstride, Gl + gb * gstride, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
         if (q.bias) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -204,11 +212,11 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
             if (warp == 1) {                               // warp-collective issue, one elected lane (tc_issue_kmajor_w)
                 uint32_t acc = ntile_done > 0 ? 1u : 0u;
                 // A = G^T (M = 128 rows = co), B = X_j^T (N rows = ci), K = 64 frames
-                tc_issue_kmajor_w<SPLIT>(tmem + j * q.Npad, gh_s, gl_s, CSG * 4, 0, tc::smem_u32(slot_hi(step % NS)),
+                tc_issue_kmajor_w<SPLIT>(tmem + j * q.Npad, gh_s + gb * gstride * 4, gl_s + gb * gstride * 4, CSG * 4, 0, tc::smem_u32(slot_hi(step % NS)),
                                          tc::smem_u32(slot_lo(step % NS)), csx * 4, CRK_WG_TF, idesc, acc);
                 if (tc::elect_one()) {
                     tc::umma_commit(&bar_slot[step % NS]);
-                    if (j == p.k - 1) tc::umma_commit(&bar_tile);
+                    if (j == p.k - 1) tc::umma_commit(&bar_tile[gb]);
                 }
                 __syncwarp();
             }
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
         ++ntile_done;
     }
     dbg_stamp(q.dbg, 4);
-    if (ntile_done > 0) ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1);
+    if (ntile_done > 0) ok &= tc::mbar_wait(&bar_tile[(ntile_done - 1) % NGB], ((ntile_done - 1) / NGB) & 1);   // (MMAs complete in order)
     tc::tc_fence_after();
     if (!ok) timeout_s = 1;
     __syncthreads();
@@ -237,9 +245,14 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     // ---- epilogue: D_j^T[co][ci] -> part[chunk][j][ci][co] ----
     const int co = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float* out = p.part + (size_t)blockIdx.x * p.part_stride;
+    float* gout = p.part + (size_t)blockIdx.x * p.part_stride;
+    // the chunk's whole partial block is assembled in shared memory (every operand buffer is free now) and leaves through
+    // ONE TMA bulk store; direct stores only when the block does not fit / is not 16 B granular
+    const bool staged = q.stage_floats >= p.part_stride + 512 && (p.part_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
+    float* out = staged ? smem : gout;
     const int nblk = (q.Npad + 31) >> 5;
     const float poison = __int_as_float(0x7fc00000);
+    // (every element of the [k][Rows][TN] (+ [TN]) block is written below: no clearing needed)
     for (int j = 0; j < p.k; ++j)
         for (int blk = warp >> 2; blk < nblk; blk += 2) {
             float v[32];
@@ -255,7 +268,7 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     if (q.bias) {
         // frames live on the 64 threads that share tid/64: warp-shuffle sum over 32 frames, then the two
         // warps of a pair through shared memory (all MMAs have completed: the G^T buffer is free)
-        float* red = smem;                                 // [8 warps][32]
+        float* red = staged ? smem + p.part_stride : smem;         // (the staged block occupies [0, part_stride))                                 // [8 warps][32]
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             float c4[4] = {bsum[u].x, bsum[u].y, bsum[u].z, bsum[u].w};
@@ -273,6 +286,14 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
             const int quad = c >> 2, g = quad & 3, u = quad >> 2;
             const float sv = red[(2 * g) * 32 + u * 4 + (c & 3)] + red[(2 * g + 1) * 32 + u * 4 + (c & 3)];
             out[(size_t)p.k * p.Rows * q.TN + c] = timeout_s ? poison : sv;
+        }
+    }
+    if (staged) {
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc::bulk_s2g(gout, smem, (uint32_t)(p.part_stride * sizeof(float)));
+            tc::bulk_commit_wait_all();
         }
     }
     tc::tc_fence_before();
@@ -510,7 +531,9 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     // ---- epilogue (workers; same layout as k_wgrad_tc) ----
     const int co = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float* out = p.part + (size_t)blockIdx.x * p.part_stride;
+    float* gout = p.part + (size_t)blockIdx.x * p.part_stride;
+    const bool staged = q.stage_floats >= p.part_stride + 512 && (p.part_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
+    float* out = staged ? smem : gout;                     // (see k_wgrad_tc: one TMA bulk store per chunk)
     const int nblk = (q.Npad + 31) >> 5;
     const float poison = __int_as_float(0x7fc00000);
     if (worker)
@@ -527,7 +550,7 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
                 }
             }
     if (q.bias) {
-        float* red = smem;
+        float* red = staged ? smem + p.part_stride : smem;         // (the staged block occupies [0, part_stride))
         if (worker) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -547,6 +570,14 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
             const int quad = c >> 2, g = quad & 3, u = quad >> 2;
             const float sv = red[(2 * g) * 32 + u * 4 + (c & 3)] + red[(2 * g + 1) * 32 + u * 4 + (c & 3)];
             out[(size_t)p.k * p.Rows * q.TN + c] = timeout_s ? poison : sv;
+        }
+    }
+    if (staged) {
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc::bulk_s2g(gout, smem, (uint32_t)(p.part_stride * sizeof(float)));
+            tc::bulk_commit_wait_all();
         }
     }
     tc::tc_fence_before();
@@ -587,19 +618,25 @@ inline cudaError_t launch_wgrad_tc_raw_nx(const WgradTcParams& q, int nchunk, cu
     const size_t g = (size_t)16 * 129 * 4 * (SPLIT ? 2 : 1), x = (size_t)16 * tc::chunk_rows(q.Npad) * 4 * (SPLIT ? 2 : 1);
     const size_t smem = (g + q.nslot * x + wgrad_raw_floats(q.Npad, q.p.k, q.p.dil, SPLIT)) * sizeof(float);
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
-    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L>, dim3(nchunk), dim3(288), smem, s, q);
+    WgradTcParams qq = q;
+    qq.stage_floats = !(opt_enable_mask() & 4) ? 0 : (long long)(smem / sizeof(float));
+    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L>, dim3(nchunk), dim3(288), smem, s, qq);
     if (le != cudaSuccess) return le;
     return launch_check();
 }
 
-inline int wgrad_tc_nslot(int Npad, bool split) {
+inline int wgrad_tc_gbuf(int Npad, bool split) {       // two G^T buffers when they fit next to two X^T slots
     const size_t g = (size_t)16 * 129 * 4 * (split ? 2 : 1), x = (size_t)16 * tc::chunk_rows(Npad) * 4 * (split ? 2 : 1);
-    size_t n = (200 * 1024 / sizeof(float) - g) / x;
+    return (2 * g + 2 * x) * sizeof(float) <= 215 * 1024 ? 2 : 1;
+}
+inline int wgrad_tc_nslot(int Npad, bool split) {
+    const size_t g = (size_t)16 * 129 * 4 * (split ? 2 : 1) * wgrad_tc_gbuf(Npad, split), x = (size_t)16 * tc::chunk_rows(Npad) * 4 * (split ? 2 : 1);
+    size_t n = (215 * 1024 / sizeof(float) - g) / x;
     return n >= 4 ? 4 : (n >= 3 ? 3 : 2);
 }
 inline size_t wgrad_tc_smem(int Npad, bool split) {
     const size_t g = (size_t)16 * 129 * 4, x = (size_t)16 * tc::chunk_rows(Npad) * 4;
-    return ((split ? 2 : 1) * g + (split ? 2 : 1) * wgrad_tc_nslot(Npad, split) * x) * sizeof(float);
+    return ((split ? 2 : 1) * wgrad_tc_gbuf(Npad, split) * g + (split ? 2 : 1) * wgrad_tc_nslot(Npad, split) * x) * sizeof(float);
 }
 inline bool wgrad_tc_ok(const WgradParams& p, int TN, int Npad, bool split) {
     return TN <= 128 && Npad >= 16 && Npad <= 128 && p.k * Npad <= 512 && p.Rows <= Npad &&  // X^T tile <= 8 float4/thread
@@ -626,7 +663,9 @@ inline cudaError_t launch_wgrad_tc_nx(const WgradTcParams& q, int nchunk, cudaSt
         attr_set = true;
     }
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
-    cudaError_t le = launch_pdl(k_wgrad_tc<SPLIT, NX, VEC>, dim3(nchunk), dim3(256), wgrad_tc_smem(q.Npad, SPLIT), s, q);
+    WgradTcParams qq = q;
+    qq.stage_floats = !(opt_enable_mask() & 4) ? 0 : (long long)(wgrad_tc_smem(q.Npad, SPLIT) / sizeof(float));
+    cudaError_t le = launch_pdl(k_wgrad_tc<SPLIT, NX, VEC>, dim3(nchunk), dim3(256), wgrad_tc_smem(q.Npad, SPLIT), s, qq);
     if (le != cudaSuccess) return le;
     return launch_check();
 }
@@ -657,6 +696,7 @@ inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, in
     const WgradTcWork w = wgrad_tc_work(p.B, p.T);
     WgradTcParams q;
     q.p = p; q.p.part = part; q.p.tiles_per_chunk = w.tiles_per_chunk; q.TN = TN; q.Npad = Npad; q.dbg = dbg_take(CRK_K_WGRAD); q.nslot = wgrad_tc_nslot(Npad, split);
+    q.gbuf = wgrad_tc_gbuf(Npad, split);
     q.bias = (fused_bias && !(opt_disable_mask() & 2)) ? 1 : 0;
     *bias_done = q.bias != 0;
     *nchunk = w.nchunk;
