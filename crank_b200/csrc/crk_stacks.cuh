@@ -221,20 +221,55 @@ inline WavenetAct wavenet_act(const crk_wavenet_cfg* c, long long F) {
     a.total = a.head1 + F * 64;
     return a;
 }
+// ---- weight gradients on a side stream (round 2) ------------------------------------------------------------------
+// With few tiles per launch (8 utterances per GPU = 32 tiles on 148 SMs: BASELINE config 3 at 8 GPUs) a step is a chain of
+// ~900 dependent kernels of ~13 us each, most SMs idle.  The weight-gradient kernels (wgrad + partial-sum reduce: 4-6 of
+// the ~8 launches of a block's backward) do not feed the dgrad chain, so they run on a side stream: fork after the kernel
+// that produces their operands (an event), join before the weight-norm backward.  Needs the per-layer operands (dg, gos,
+// z) to stay alive until their wgrad ran: one buffer per layer instead of one per stack.  Only when tiles <= SMs / 2: on
+// full launches the wgrad CTAs (200 KB of shared memory) would just take SMs from the dgrad chain.
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[64];
+    bool ok = false;
+};
+inline SideStream* side_stream() {
+    static thread_local SideStream S;
+    if (!S.ok) {
+        if (cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 64; ++i)
+            if (cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        S.ok = true;
+    }
+    return &S;
+}
+inline bool wavenet_side_mode(int B, int T) {
+    return !(opt_disable_mask() & 512) && 2 * B * cdiv(T, CRK_TC_TM) <= device_sm_count();
+}
+// `to` waits for everything `from` has been given so far
+inline cudaError_t stream_fork(SideStream* S, int& evn, cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = S->ev[evn++ & 63];
+    cudaError_t rc = cudaEventRecord(e, from);
+    if (rc != cudaSuccess) return rc;
+    return cudaStreamWaitEvent(to, e, 0);
+}
+
 struct WavenetWs {
     long long gweff, dhA, dhB, ds, dg, gos, z, dhead1, part, total;
+    int nb;             // per-layer copies of dg / gos / z (1, or `layers` in side-stream mode)
 };
 inline WavenetWs wavenet_ws(const crk_wavenet_cfg* c, const WavenetLayout& L, int B, int T) {
     const long long F = (long long)B * T;
     WavenetWs w;
+    w.nb = wavenet_side_mode(B, T) ? c->layers : 1;
     w.gweff = 0;
     w.dhA = round_up((int)L.weff, 4);
     w.dhB = w.dhA + F * 64;
     w.ds = w.dhB + F * 64;
     w.dg = w.ds + F * 64;
-    w.gos = w.dg + F * 128;
-    w.z = w.gos + F * 128;
-    w.dhead1 = w.z + F * 64;
+    w.gos = w.dg + (long long)w.nb * F * 128;
+    w.z = w.gos + (long long)w.nb * F * 128;
+    w.dhead1 = w.z + (long long)w.nb * F * 64;
     w.part = w.dhead1 + F * 64;
     size_t m = 0;
     for (int i = 0; i < L.tab.n; ++i) {
@@ -347,6 +382,12 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
     const float* head1 = act + A.head1;
     const float hscale = sqrtf(1.0f / (float)c->layers);
     const int cpt_out = cpt_for(c->out_ch);
+    // side-stream mode: every wgrad (+ reduce) goes to `sw`, forked from `s` after its operands were produced
+    SideStream* SS = (need_w && W.nb > 1) ? side_stream() : nullptr;
+    const bool side = SS != nullptr;
+    cudaStream_t sw = side ? SS->st : s;
+    int evn = 0;
+    if (side) CRK_TRY(stream_fork(SS, evn, s, sw));       // (dy and the saved activations are ready on `s`)
 
     // ---- head: y = W2.act(head1)+b2 ; head1 = W1.act(hscale*skips)+b1
     {
@@ -355,12 +396,13 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
         g.X = head1; g.ldx = 64; g.Cin = 64; g.Rows = 64;
         g.pro_act = c->head_act; g.pro_slope = c->slope; g.pro_scale = 1.f; g.xmul = nullptr; g.ldxmul = 0;
         g.G = dy; g.ldg = lddy; g.N = c->out_ch; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-        if (need_w) CRK_TRY(conv_wgrad(g, cpt_out, gweff + d.w_off, gweff + d.bias_off, part, s));
+        if (need_w) CRK_TRY(conv_wgrad(g, cpt_out, gweff + d.w_off, gweff + d.bias_off, part, sw));
         ConvParams p = conv_params_default();   // dhead1 = (dy . W2^T) * act'(head1)
         p.X = dy; p.ldx = lddy; p.Cin = c->out_ch; p.CinPad = d.wt_rows;
         p.W = weff + d.wt_off; p.Y = ws + W.dhead1; p.ldy = 64; p.Cout = 64; p.B = B; p.T = T;
         p.dact_src = head1; p.lddact = 64; p.dact_mode = c->head_act; p.dact_slope = c->slope;
         CRK_TRY(conv_dispatch(p, 2, weff + d.tct_off, d.tct_kpad, d.tct_n, s));
+        if (side) CRK_TRY(stream_fork(SS, evn, s, sw));   // dhead1 -> wgrad(last1)
     }
     {
         const crk_conv_desc& d = L.tab.d[L.last1];
@@ -368,7 +410,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
         g.X = skips; g.ldx = 64; g.Cin = 64; g.Rows = 64;
         g.pro_act = c->head_act; g.pro_slope = c->slope; g.pro_scale = hscale; g.xmul = nullptr; g.ldxmul = 0;
         g.G = ws + W.dhead1; g.ldg = 64; g.N = 64; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-        if (need_w) CRK_TRY(conv_wgrad(g, 2, gweff + d.w_off, gweff + d.bias_off, part, s));
+        if (need_w) CRK_TRY(conv_wgrad(g, 2, gweff + d.w_off, gweff + d.bias_off, part, sw));
         ConvParams p = conv_params_default();   // ds = (dhead1 . W1^T) * act'(skips) * hscale
         p.X = ws + W.dhead1; p.ldx = 64; p.Cin = 64; p.CinPad = 64;
         p.W = weff + d.wt_off; p.Y = ws + W.ds; p.ldy = 64; p.Cout = 64; p.B = B; p.T = T;
@@ -385,42 +427,47 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
         const int padl = wn_padl(c, dil);
         const float* hin = h + (long long)l * F * 64;
         const float* dm = dropmul ? dropmul + (long long)l * F * 64 : nullptr;
+        const long long lb = (long long)(l % W.nb);           // this layer's dg / gos / z buffers
+        float* DGl = ws + W.dg + lb * F * 128;
+        float* GOSl = ws + W.gos + lb * F * 128;
+        float* Zl = ws + W.z + lb * F * 64;
         {
             ResBwdGateParams p;
             p.dH = dh_cur; p.dS = ws + W.ds; p.TaSb = act + A.tasb + (long long)l * F * 128;
             p.WosT = weff + L.tab.d[L.out[l]].wt_off;
-            p.DG = ws + W.dg; p.GOS = ws + W.gos; p.Z = ws + W.z; p.B = B; p.T = T;
+            p.DG = DGl; p.GOS = GOSl; p.Z = Zl; p.B = B; p.T = T;
             cudaError_t ge = cudaSuccess;
             if (gate_bwd_tc(p, weff + L.tab.d[L.out[l]].tct_off, s, &ge)) CRK_TRY(ge);
             else CRK_TRY(launch_resblock_bwd_gate(p, s));
+            if (side) CRK_TRY(stream_fork(SS, evn, s, sw));   // dg / gos / z of this layer -> its three wgrads
         }
         {   // [out|skip] weights:  dWos = z^T . gos
             const crk_conv_desc& d = L.tab.d[L.out[l]];
             WgradParams g;
-            g.X = ws + W.z; g.ldx = 64; g.Cin = 64; g.Rows = 64;
+            g.X = Zl; g.ldx = 64; g.Cin = 64; g.Rows = 64;
             g.pro_act = CRK_ACT_NONE; g.pro_slope = 0.f; g.pro_scale = 1.f; g.xmul = nullptr; g.ldxmul = 0;
-            g.G = ws + W.gos; g.ldg = 128; g.N = 128; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-            if (need_w) CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, gweff + d.bias_off, part, s));
+            g.G = GOSl; g.ldg = 128; g.N = 128; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
+            if (need_w) CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, gweff + d.bias_off, part, sw));
         }
         {   // dilated conv weights
             const crk_conv_desc& d = L.tab.d[L.conv[l]];
             WgradParams g;
             g.X = hin; g.ldx = 64; g.Cin = 64; g.Rows = 64;
             g.pro_act = CRK_ACT_NONE; g.pro_slope = 0.f; g.pro_scale = 1.f; g.xmul = dm; g.ldxmul = 64;
-            g.G = ws + W.dg; g.ldg = 128; g.N = 128; g.B = B; g.T = T;
+            g.G = DGl; g.ldg = 128; g.N = 128; g.B = B; g.T = T;
             g.k = c->kernel_size; g.dil = dil; g.padl = padl;
-            if (need_w) CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, gweff + d.bias_off, part, s));
+            if (need_w) CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, gweff + d.bias_off, part, sw));
         }
         if (c->aux_ch > 0) {
             const crk_conv_desc& d = L.tab.d[L.aux[l]];
             WgradParams g;
             g.X = cond; g.ldx = ldc; g.Cin = c->aux_ch; g.Rows = d.cin_pad;
             g.pro_act = CRK_ACT_NONE; g.pro_slope = 0.f; g.pro_scale = 1.f; g.xmul = nullptr; g.ldxmul = 0;
-            g.G = ws + W.dg; g.ldg = 128; g.N = 128; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-            if (need_w) CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, nullptr, part, s));
+            g.G = DGl; g.ldg = 128; g.N = 128; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
+            if (need_w) CRK_TRY(conv_wgrad(g, 4, gweff + d.w_off, nullptr, part, sw));
             if (dc) {
                 ConvParams p = conv_params_default();
-                p.X = ws + W.dg; p.ldx = 128; p.Cin = 128; p.CinPad = 128;
+                p.X = DGl; p.ldx = 128; p.Cin = 128; p.CinPad = 128;
                 p.W = weff + d.wt_off; p.Y = dc; p.ldy = lddc; p.Cout = c->aux_ch; p.B = B; p.T = T;
                 p.accumulate = (l != c->layers - 1);
                 CRK_TRY(conv_dispatch(p, cpt_for(c->aux_ch), weff + d.tct_off, d.tct_kpad, d.tct_n, s));
@@ -430,7 +477,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
             const crk_conv_desc& d = L.tab.d[L.conv[l]];
             float* dst = dh_bufs[flip];
             ConvParams p = conv_params_default();
-            p.X = ws + W.dg; p.ldx = 128; p.Cin = 128; p.CinPad = 128;
+            p.X = DGl; p.ldx = 128; p.Cin = 128; p.CinPad = 128;
             p.W = weff + d.wt_off; p.Y = dst; p.ldy = 64; p.Cout = 64; p.B = B; p.T = T;
             p.k = c->kernel_size; p.dil = dil; p.padl = (c->kernel_size - 1) * dil - padl;
             p.mul_src = dm; p.ldmul = 64;
@@ -450,7 +497,8 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
         g.X = x; g.ldx = ldx; g.Cin = c->in_ch; g.Rows = d.cin_pad;
         g.pro_act = CRK_ACT_NONE; g.pro_slope = 0.f; g.pro_scale = 1.f; g.xmul = nullptr; g.ldxmul = 0;
         g.G = dh_cur; g.ldg = 64; g.N = 64; g.B = B; g.T = T; g.k = 1; g.dil = 1; g.padl = 0;
-        if (need_w) CRK_TRY(conv_wgrad(g, 2, gweff + d.w_off, gweff + d.bias_off, part, s));
+        if (side) CRK_TRY(stream_fork(SS, evn, s, sw));       // the input gradient of layer 0 -> wgrad(first)
+        if (need_w) CRK_TRY(conv_wgrad(g, 2, gweff + d.w_off, gweff + d.bias_off, part, sw));
         if (dx) {
             ConvParams p = conv_params_default();
             p.X = dh_cur; p.ldx = 64; p.Cin = 64; p.CinPad = 64;
@@ -458,6 +506,7 @@ inline int wavenet_bwd(const crk_wavenet_cfg* c, const float* theta, const float
             CRK_TRY(conv_dispatch(p, cpt_for(c->in_ch), weff + d.tct_off, d.tct_kpad, d.tct_n, s));
         }
     }
+    if (side) CRK_TRY(stream_fork(SS, evn, sw, s));           // join: every weight gradient is complete
     if (need_w) CRK_TRY(launch_weightnorm_bwd(L.tab, theta, gweff, gtheta, s));
     return CRK_OK;
 }
