@@ -73,6 +73,7 @@ inline int& tc_disable_mask() { static int m = 0; return m; }
 //   32 persistent pipelined conv / dgrad (k_conv_pt) off -> k_conv_tc
 //   64 two-CTA/SM fused forward (k_resblock_fwd_tc2) off -> round 1's k_resblock_fwd_tc
 //   128 two-CTA/SM K-phased k_conv_tc off -> whole-K variant (one CTA per SM in the 3xTF32 mode)
+//   1024 16 worker warps in k_wgrad_tc_raw off -> 8
 //   512 weight gradients of small launches on a side stream (crk_stacks.cuh wavenet_bwd) off -> everything on the caller's stream
 inline int& opt_disable_mask() { static int m = 0; return m; }
 // opt-IN switches (crk_debug_opt_enable / CRANK_B200_OPT_ENABLE): experimental paths that are correct (parity-tested)

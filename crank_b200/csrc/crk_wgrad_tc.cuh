@@ -43,7 +43,7 @@ struct WgRegs {
 };
 
 // VECONLY: host-checked (16 B aligned rows, ncols % 4 == 0) -> the scalar tail path is compiled out
-template <int NB, bool VECONLY = false>
+template <int NB, bool VECONLY = false, int TW = 256>
 __device__ __forceinline__ void wg_load(WgRegs<NB>& R, int nrows_pad, const float* __restrict__ src, int ld, int ncols,
                                         int b, int T, int t0, int shift, const float* __restrict__ mul, int ldmul) {
     const int total = CRK_WG_TF * (nrows_pad >> 2);
@@ -51,7 +51,7 @@ __device__ __forceinline__ void wg_load(WgRegs<NB>& R, int nrows_pad, const floa
                      (mul == nullptr || (((ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mul) & 15) == 0))));
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
-        const int idx = threadIdx.x + u * 256;
+        const int idx = threadIdx.x + u * TW;
         R.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         R.m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
         if (idx < total) {
@@ -80,13 +80,13 @@ __device__ __forceinline__ void wg_load(WgRegs<NB>& R, int nrows_pad, const floa
     }
 }
 
-template <bool SPLIT, int NB>
+template <bool SPLIT, int NB, int TW = 256>
 __device__ __forceinline__ void wg_store(const WgRegs<NB>& R, float* hi, float* lo, int cs_floats, int nrows_pad,
                                          int pro_act, float pro_slope, float pro_scale) {
     const int total = CRK_WG_TF * (nrows_pad >> 2);
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
-        const int idx = threadIdx.x + u * 256;
+        const int idx = threadIdx.x + u * TW;
         if (idx >= total) continue;
         const int c4 = idx >> 6, f = idx & 63;
         const int off = (f >> 2) * cs_floats + c4 * 16 + (f & 3);
@@ -314,7 +314,7 @@ __host__ __device__ inline size_t wgrad_raw_half(int Npad, int k, int dil) { ret
 //   bank groups), r <-> input time t0 - padl + r, zero outside [0, T).
 // C4L: log2(c4n) when the channel-quad count is a power of two (the index split becomes a shift; the runtime
 // division cost ~1.8K cycles per tile in the load-issue and store phases each), -1: generic
-template <int NR, bool VECONLY, int C4L>
+template <int NR, bool VECONLY, int C4L, int TW = 256>
 __device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, const float* __restrict__ src, int ld,
                                             int ncols, int b, int T, int tstart, const float* __restrict__ mul, int ldmul) {
     const int total = rows * c4n;
@@ -322,7 +322,7 @@ __device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, co
                      (mul == nullptr || (((ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mul) & 15) == 0))));
 #pragma unroll
     for (int u = 0; u < NR; ++u) {
-        const int idx = threadIdx.x + u * 256;
+        const int idx = threadIdx.x + u * TW;
         R.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         R.m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
         if (idx < total) {
@@ -353,13 +353,13 @@ __device__ __forceinline__ void wg_load_raw(WgRegs<NR>& R, int c4n, int rows, co
 // SPLIT: the hi / lo parts are produced HERE, once per input element, into two raw copies (xraw | xraw_lo): round 1 re-split
 // the same element for every one of the k taps that read it (ncu, round 2: the split arithmetic + its stores were ~40 % of
 // the kernel's issue slots for k = 5)
-template <bool SPLIT, int NR, int C4L>
+template <bool SPLIT, int NR, int C4L, int TW = 256>
 __device__ __forceinline__ void wg_store_raw(const WgRegs<NR>& R, float* xraw, float* xraw_lo, int stride, int c4n, int rows,
                                              int pro_act, float pro_slope, float pro_scale) {
     const int total = rows * c4n;
 #pragma unroll
     for (int u = 0; u < NR; ++u) {
-        const int idx = threadIdx.x + u * 256;
+        const int idx = threadIdx.x + u * TW;
         if (idx >= total) continue;
         const int r = C4L >= 0 ? (idx >> (C4L >= 0 ? C4L : 0)) : idx / c4n, c4 = idx - r * c4n;
         float4 x;
@@ -380,13 +380,13 @@ __device__ __forceinline__ void wg_store_raw(const WgRegs<NR>& R, float* xraw, f
 }
 
 // transposed hi/lo operand tile of one tap from the raw rows: elem(frame f, channel c) = xraw[f + shift][c]
-template <bool SPLIT, int NX>
+template <bool SPLIT, int NX, int TW = 256>
 __device__ __forceinline__ void wg_transpose_raw(const float* xraw, const float* xraw_lo, int stride, float* hi, float* lo,
                                                  int cs_floats, int nrows_pad, int shift) {
     const int total = CRK_WG_TF * (nrows_pad >> 2);
 #pragma unroll
     for (int u = 0; u < NX; ++u) {
-        const int idx = threadIdx.x + u * 256;
+        const int idx = threadIdx.x + u * TW;
         if (idx >= total) continue;
         const int c4 = idx >> 6, f = idx & 63;
         const float4 v = *reinterpret_cast<const float4*>(xraw + (f + shift) * stride + c4 * 4);
@@ -399,14 +399,21 @@ __device__ __forceinline__ void wg_transpose_raw(const float* xraw, const float*
     }
 }
 
-template <bool SPLIT, int NX, bool VEC, int C4L>
-__global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) {
+// TW worker threads (+ one issuer warp).  Round 2: TW = 512 -- with 8 worker warps (2 per scheduler) the per-tile stores, address
+// arithmetic and transpositions ran at 6-20 cycles per instruction (measured per phase: G store 1.4 K, raw store 3.0 K, issuing
+// the next tile's loads 4.1 K, 5 tap transpositions 4.1 K cycles for ~500 instructions per thread): latency-bound issue, not
+// throughput.  16 worker warps halve the per-thread work at the same total.
+template <bool SPLIT, int NX, bool VEC, int C4L, int TW>
+__global__ void __launch_bounds__(TW + 32, 1) k_wgrad_tc_raw(const WgradTcParams q) {
     // 9 warps: warps 0..7 ("workers") load, stage and transpose; warp 8 only issues MMAs.  With the issue
     // inside a worker warp every tap waited ~1K cycles at the block barrier for that warp's 24 MMAs
     // (measured: 19K of 85K cycles per CTA); now workers hand a finished slot to the issuer through an
     // mbarrier and go straight to the next tap.
-    constexpr int NR = NX == 4 ? 6 : 10;                   // raw-tile float4 per thread (host checks the fit)
-    constexpr int NWORK = 256;
+    constexpr int SC = TW / 256;                           // worker scale
+    constexpr int NR = (NX == 4 ? 6 : 10) / SC;            // raw-tile float4 per thread (host checks the fit)
+    constexpr int NG = 8 / SC;                             // G-tile float4 per thread
+    constexpr int NT = NX / SC;                            // tap-tile float4 per thread
+    constexpr int NWORK = TW;
     const WgradParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
@@ -453,20 +460,20 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     const uint32_t tmem = tmem_base_s;
     bool ok = true;
     int ntile_done = 0;
-    float4 bsum[8];
+    float4 bsum[NG];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) bsum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < NG; ++u) bsum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     pdl_trigger();                                      // only now: this CTA already owns its TMEM columns (see crk_common.cuh)
     pdl_wait();
 
     if (worker) {
-        WgRegs<8> RG;
+        WgRegs<NG> RG;
         WgRegs<NR> RX;
         auto load_tile = [&](int tile) {
             const int bb = tile / tiles_per_utt;
             const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
-            wg_load<8, VEC>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
-            wg_load_raw<NR, VEC, C4L>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
+            wg_load<NG, VEC, TW>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
+            wg_load_raw<NR, VEC, C4L, TW>(RX, c4n, rows_raw, p.X, p.ldx, p.Cin, bb, p.T, tt0 - p.padl, p.xmul, p.ldxmul);
         };
         int step = 0;
         if (tile_beg < tile_end) load_tile(tile_beg);
@@ -474,27 +481,42 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
             if (tile == tile_beg) dbg_stamp(q.dbg, 0);
             // the previous tile's MMAs read the G^T buffer and the ring slots; they were issued only after
             // every worker had handed over its last slot, i.e. finished reading xraw -> all three are free
+            const bool dbg1 = q.dbg && tile == tile_beg + 1 && threadIdx.x == 64;      // second tile: steady-state phase costs
+            const long long c0 = dbg1 ? clock64() : 0;
             if (ntile_done > 0) { ok &= tc::mbar_wait(&bar_tile, (ntile_done - 1) & 1); tc::tc_fence_after(); }
             if (tile == tile_beg) dbg_stamp(q.dbg, 1);
-            wg_store<SPLIT, 8>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
+            const long long c1 = dbg1 ? clock64() : 0;
+            wg_store<SPLIT, NG, TW>(RG, Gh, Gl, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
             if (q.bias) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < NG; ++u) {
                     bsum[u].x += RG.v[u].x; bsum[u].y += RG.v[u].y; bsum[u].z += RG.v[u].z; bsum[u].w += RG.v[u].w;
                 }
             }
-            wg_store_raw<SPLIT, NR, C4L>(RX, xraw, xraw_lo, rstride, c4n, rows_raw, p.pro_act, p.pro_slope, p.pro_scale);
+            const long long c2 = dbg1 ? clock64() : 0;
+            wg_store_raw<SPLIT, NR, C4L, TW>(RX, xraw, xraw_lo, rstride, c4n, rows_raw, p.pro_act, p.pro_slope, p.pro_scale);
+            const long long c3 = dbg1 ? clock64() : 0;
             if (tile + 1 < tile_end) load_tile(tile + 1);  // a whole tile (k tap iterations) of latency cover
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // workers only: xraw complete
+            const long long c4 = dbg1 ? clock64() : 0;
+            asm volatile("bar.sync 1, %0;" ::"n"(TW) : "memory");  // workers only: xraw complete
+            if (dbg1) {
+                const long long c5 = clock64();
+                dbg_put(1, 11, c1 - c0); dbg_put(1, 12, c2 - c1); dbg_put(1, 13, c3 - c2); dbg_put(1, 14, c4 - c3); dbg_put(1, 15, c5 - c4);
+            }
             if (tile == tile_beg) dbg_stamp(q.dbg, 2);
+            long long tw = 0, tt = 0;
             for (int j = 0; j < p.k; ++j, ++step) {
                 const int sl = step % NS;
+                const long long d0 = dbg1 ? clock64() : 0;
                 // the MMAs of step - NS (this tile; earlier tiles are covered by bar_tile) read this slot
                 if (j >= NS) ok &= tc::mbar_wait(&bar_slot[sl], ((step - NS) / NS) & 1);
-                wg_transpose_raw<SPLIT, NX>(xraw, xraw_lo, rstride, slot_hi(sl), slot_lo(sl), csx, q.Npad, j * p.dil);
+                const long long d1 = dbg1 ? clock64() : 0;
+                wg_transpose_raw<SPLIT, NT, TW>(xraw, xraw_lo, rstride, slot_hi(sl), slot_lo(sl), csx, q.Npad, j * p.dil);
                 tc::fence_proxy_async_smem();               // generic-proxy writes (G^T, slot) -> async proxy
                 tc::mbar_arrive(&bar_full[sl]);
+                if (dbg1) { tw += d1 - d0; tt += clock64() - d1; }
             }
+            if (dbg1) { dbg_put(1, 8, tw); dbg_put(1, 9, tt); }
             if (tile == tile_beg) dbg_stamp(q.dbg, 3);
             ++ntile_done;
         }
@@ -537,23 +559,23 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
     const int nblk = (q.Npad + 31) >> 5;
     const float poison = __int_as_float(0x7fc00000);
     if (worker)
-        for (int j = 0; j < p.k; ++j)
-            for (int blk = warp >> 2; blk < nblk; blk += 2) {
-                float v[32];
-                if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
-                if (co >= q.TN) continue;
+        for (int pair = warp >> 2; pair < p.k * nblk; pair += TW / 128) {      // (tap j, 32-column block) pairs over the worker warps
+            const int j = pair / nblk, blk = pair - j * nblk;
+            float v[32];
+            if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
+            if (co >= q.TN) continue;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int ci = blk * 32 + i;
-                    if (ci < p.Rows)
-                        out[((size_t)j * p.Rows + ci) * q.TN + co] = timeout_s ? poison : (ntile_done > 0 ? v[i] : 0.f);
-                }
+            for (int i = 0; i < 32; ++i) {
+                const int ci = blk * 32 + i;
+                if (ci < p.Rows)
+                    out[((size_t)j * p.Rows + ci) * q.TN + co] = timeout_s ? poison : (ntile_done > 0 ? v[i] : 0.f);
             }
+        }
     if (q.bias) {
         float* red = staged ? smem + p.part_stride : smem;         // (the staged block occupies [0, part_stride))
         if (worker) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < NG; ++u) {
                 float c4[4] = {bsum[u].x, bsum[u].y, bsum[u].z, bsum[u].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -566,8 +588,9 @@ __global__ void __launch_bounds__(288, 1) k_wgrad_tc_raw(const WgradTcParams q) 
         }
         __syncthreads();
         if (threadIdx.x < q.TN) {
-            const int c = threadIdx.x;
-            const int quad = c >> 2, g = quad & 3, u = quad >> 2;
+            const int c = threadIdx.x;                     // G column: quad c/4 = g + (TW/64) u  (g = tid/64 of its owners)
+            constexpr int GQ = TW / 64;
+            const int quad = c >> 2, g = quad & (GQ - 1), u = quad / GQ;
             const float sv = red[(2 * g) * 32 + u * 4 + (c & 3)] + red[(2 * g + 1) * 32 + u * 4 + (c & 3)];
             out[(size_t)p.k * p.Rows * q.TN + c] = timeout_s ? poison : sv;
         }
@@ -598,7 +621,7 @@ inline int wgrad_raw_nslot(int Npad, int k, int dil, bool split) {
 }
 inline bool wgrad_raw_ok(const WgradParams& p, int Npad, bool split) {
     if (p.k < 2 || (opt_disable_mask() & 8)) return false;
-    const int nr = Npad <= 64 ? 6 : 10;
+    const int nr = Npad <= 64 ? 6 : 10;                    // per thread at 256 workers (3 / 5 at 512: the same total)
     if ((CRK_WG_TF + (p.k - 1) * p.dil) * (Npad >> 2) > nr * 256) return false;
     return wgrad_raw_nslot(Npad, p.k, p.dil, split) >= 2;
 }
@@ -607,11 +630,11 @@ inline bool wgrad_vec_ok(const WgradParams& p) {
     auto al = [](const float* ptr, int ld) { return ptr == nullptr || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0)); };
     return (p.Cin & 3) == 0 && (p.N & 3) == 0 && al(p.X, p.ldx) && al(p.G, p.ldg) && al(p.xmul, p.ldxmul);
 }
-template <bool SPLIT, int NX, bool VEC, int C4L>
-inline cudaError_t launch_wgrad_tc_raw_nx(const WgradTcParams& q, int nchunk, cudaStream_t s) {
+template <bool SPLIT, int NX, bool VEC, int C4L, int TW>
+inline cudaError_t launch_wgrad_tc_raw_tw(const WgradTcParams& q, int nchunk, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -620,9 +643,15 @@ inline cudaError_t launch_wgrad_tc_raw_nx(const WgradTcParams& q, int nchunk, cu
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
     WgradTcParams qq = q;
     qq.stage_floats = !(opt_enable_mask() & 4) ? 0 : (long long)(smem / sizeof(float));
-    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L>, dim3(nchunk), dim3(288), smem, s, qq);
+    cudaError_t le = launch_pdl(k_wgrad_tc_raw<SPLIT, NX, VEC, C4L, TW>, dim3(nchunk), dim3(TW + 32), smem, s, qq);
     if (le != cudaSuccess) return le;
     return launch_check();
+}
+template <bool SPLIT, int NX, bool VEC, int C4L>
+inline cudaError_t launch_wgrad_tc_raw_nx(const WgradTcParams& q, int nchunk, cudaStream_t s) {
+    // 512 workers need the per-thread counts (8 G, 6 / 10 raw, NX tap float4 at 256 workers) to halve evenly: NX = 4 and 8 both do
+    if (opt_disable_mask() & 1024) return launch_wgrad_tc_raw_tw<SPLIT, NX, VEC, C4L, 256>(q, nchunk, s);
+    return launch_wgrad_tc_raw_tw<SPLIT, NX, VEC, C4L, 512>(q, nchunk, s);
 }
 
 inline int wgrad_tc_gbuf(int Npad, bool split) {       // two G^T buffers when they fit next to two X^T slots
