@@ -108,8 +108,11 @@ __device__ __forceinline__ void wg_store(const WgRegs<NB>& R, float* hi, float* 
     }
 }
 
-template <bool SPLIT, int NX, bool VEC>
-__global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(const WgradTcParams q) {
+// TW threads: 512 in the 3xTF32 mode since round 2 (see k_wgrad_tc_raw: the per-tile stores are latency-bound with 8 warps)
+template <bool SPLIT, int NX, bool VEC, int TW>
+__global__ void __launch_bounds__(TW, (SPLIT || NX > 4 || TW > 256) ? 1 : 2) k_wgrad_tc(const WgradTcParams q) {
+    constexpr int SC = TW / 256;
+    constexpr int NG = 8 / SC, NXT = NX / SC;              // G^T / X^T float4 per thread
     const WgradParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
@@ -160,28 +163,28 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     // G^T tile = 64 frames x 128 channels = 8 float4 per thread; X^T tile = NX float4 per thread (4 when
     // Npad <= 64).  The X loads of tap j+1 are issued BEFORE the MMAs of tap j are even launched and land
     // while the previous tap is stored / synchronised; G of the next tile is prefetched during the last tap.
-    WgRegs<8> RG;
-    WgRegs<NX> RX;
+    WgRegs<NG> RG;
+    WgRegs<NXT> RX;
     // bias gradient: every G element passes through this thread's registers exactly once (wg_load of the
     // tile), always the same (frame f = tid & 63, channel quad tid/64 + 4u) slot -> per-thread running
     // sums, combined once per CTA in fixed order (deterministic); no second pass over G
-    float4 bsum[8];
+    float4 bsum[NG];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) bsum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < NG; ++u) bsum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     pdl_trigger();                                      // only now: this CTA already owns its TMEM columns (see crk_common.cuh)
     pdl_wait();
     auto load_x = [&](int tile, int j) {
         const int bb = tile / tiles_per_utt;
         const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
-        wg_load<NX, VEC>(RX, q.Npad, p.X, p.ldx, p.Cin, bb, p.T, tt0, j * p.dil - p.padl, p.xmul, p.ldxmul);
+        wg_load<NXT, VEC, TW>(RX, q.Npad, p.X, p.ldx, p.Cin, bb, p.T, tt0, j * p.dil - p.padl, p.xmul, p.ldxmul);
     };
     auto store_x = [&](int slot) {
-        wg_store<SPLIT, NX>(RX, slot_hi(slot), slot_lo(slot), csx, q.Npad, p.pro_act, p.pro_slope, p.pro_scale);
+        wg_store<SPLIT, NXT, TW>(RX, slot_hi(slot), slot_lo(slot), csx, q.Npad, p.pro_act, p.pro_slope, p.pro_scale);
     };
     auto load_g = [&](int tile) {
         const int bb = tile / tiles_per_utt;
         const int tt0 = (tile - bb * tiles_per_utt) * CRK_WG_TF;
-        wg_load<8, VEC>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
+        wg_load<NG, VEC, TW>(RG, 128, p.G, p.ldg, p.N, bb, p.T, tt0, 0, nullptr, 0);
     };
 
     if (tile_beg < tile_end) { load_g(tile_beg); load_x(tile_beg, 0); }
@@ -193,10 +196,10 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
         if (guse > 0) { ok &= tc::mbar_wait(&bar_tile[gb], (guse - 1) & 1); tc::tc_fence_after(); }
         if (step >= NS) { ok &= tc::mbar_wait(&bar_slot[step % NS], ((step - NS) / NS) & 1); tc::tc_fence_after(); }
         if (tile == tile_beg) dbg_stamp(q.dbg, 1);
-        wg_store<SPLIT, 8>(RG, Gh + gb * gstride, Gl + gb * gstride, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
+        wg_store<SPLIT, NG, TW>(RG, Gh + gb * gstride, Gl + gb * gstride, CSG, 128, CRK_ACT_NONE, 0.f, 1.f);
         if (q.bias) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < NG; ++u) {
                 bsum[u].x += RG.v[u].x; bsum[u].y += RG.v[u].y; bsum[u].z += RG.v[u].z; bsum[u].w += RG.v[u].w;
             }
         }
@@ -253,24 +256,24 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
     const int nblk = (q.Npad + 31) >> 5;
     const float poison = __int_as_float(0x7fc00000);
     // (every element of the [k][Rows][TN] (+ [TN]) block is written below: no clearing needed)
-    for (int j = 0; j < p.k; ++j)
-        for (int blk = warp >> 2; blk < nblk; blk += 2) {
-            float v[32];
-            if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
-            if (co >= q.TN) continue;
+    for (int pair = warp >> 2; pair < p.k * nblk; pair += TW / 128) {          // (tap j, 32-column block) pairs over the warps
+        const int j = pair / nblk, blk = pair - j * nblk;
+        float v[32];
+        if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
+        if (co >= q.TN) continue;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int ci = blk * 32 + i;
-                if (ci < p.Rows)
-                    out[((size_t)j * p.Rows + ci) * q.TN + co] = timeout_s ? poison : (ntile_done > 0 ? v[i] : 0.f);
-            }
+        for (int i = 0; i < 32; ++i) {
+            const int ci = blk * 32 + i;
+            if (ci < p.Rows)
+                out[((size_t)j * p.Rows + ci) * q.TN + co] = timeout_s ? poison : (ntile_done > 0 ? v[i] : 0.f);
         }
+    }
     if (q.bias) {
         // frames live on the 64 threads that share tid/64: warp-shuffle sum over 32 frames, then the two
         // warps of a pair through shared memory (all MMAs have completed: the G^T buffer is free)
         float* red = staged ? smem + p.part_stride : smem;         // (the staged block occupies [0, part_stride))                                 // [8 warps][32]
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < NG; ++u) {
             float c4[4] = {bsum[u].x, bsum[u].y, bsum[u].z, bsum[u].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -282,8 +285,9 @@ __global__ void __launch_bounds__(256, (SPLIT || NX > 4) ? 1 : 2) k_wgrad_tc(con
         }
         __syncthreads();
         if (threadIdx.x < q.TN) {
-            const int c = threadIdx.x;                     // G column: quad c/4 = g + 4u (g = tid/64 of its owners)
-            const int quad = c >> 2, g = quad & 3, u = quad >> 2;
+            const int c = threadIdx.x;                     // G column: quad c/4 = g + (TW/64) u (g = tid/64 of its owners)
+            constexpr int GQ = TW / 64;
+            const int quad = c >> 2, g = quad & (GQ - 1), u = quad / GQ;
             const float sv = red[(2 * g) * 32 + u * 4 + (c & 3)] + red[(2 * g + 1) * 32 + u * 4 + (c & 3)];
             out[(size_t)p.k * p.Rows * q.TN + c] = timeout_s ? poison : sv;
         }
@@ -683,20 +687,25 @@ inline WgradTcWork wgrad_tc_work(int B, int T) {
     return w;
 }
 
-template <bool SPLIT, int NX, bool VEC>
-inline cudaError_t launch_wgrad_tc_nx(const WgradTcParams& q, int nchunk, cudaStream_t s) {
+template <bool SPLIT, int NX, bool VEC, int TW>
+inline cudaError_t launch_wgrad_tc_tw(const WgradTcParams& q, int nchunk, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<SPLIT, NX, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc<SPLIT, NX, VEC, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     TimedLaunch tl(CRK_K_WGRAD, s, 2.0 * q.p.B * q.p.T * q.p.Cin * q.p.N * q.p.k);
     WgradTcParams qq = q;
     qq.stage_floats = !(opt_enable_mask() & 4) ? 0 : (long long)(wgrad_tc_smem(q.Npad, SPLIT) / sizeof(float));
-    cudaError_t le = launch_pdl(k_wgrad_tc<SPLIT, NX, VEC>, dim3(nchunk), dim3(256), wgrad_tc_smem(q.Npad, SPLIT), s, qq);
+    cudaError_t le = launch_pdl(k_wgrad_tc<SPLIT, NX, VEC, TW>, dim3(nchunk), dim3(TW), wgrad_tc_smem(q.Npad, SPLIT), s, qq);
     if (le != cudaSuccess) return le;
     return launch_check();
+}
+template <bool SPLIT, int NX, bool VEC>
+inline cudaError_t launch_wgrad_tc_nx(const WgradTcParams& q, int nchunk, cudaStream_t s) {
+    if (SPLIT && !(opt_disable_mask() & 1024)) return launch_wgrad_tc_tw<SPLIT, NX, VEC, 512>(q, nchunk, s);
+    return launch_wgrad_tc_tw<SPLIT, NX, VEC, 256>(q, nchunk, s);
 }
 template <bool SPLIT>
 inline cudaError_t launch_wgrad_tc_t(const WgradTcParams& q, int nchunk, cudaStream_t s) {

@@ -13,4 +13,4 @@ except Exception as e:
     print("bench failed", e); print(open("gpurun_out/r2_bench_26_m$M.err").read()[-1500:])
 PY
 done
-timeout 200 python profiles/phase_probe.py tf32x3 2>&1 | grep -v Warn | grep -B2 "wgrad conv" | cut -c1-600
+timeout 200 python profiles/phase_probe.py tf32x3 2>&1 | grep -v Warn | grep -B2 "wgrad" | cut -c1-600
