@@ -79,6 +79,7 @@ inline int& opt_disable_mask() { static int m = 0; return m; }
 // opt-IN switches (crk_debug_opt_enable / CRANK_B200_OPT_ENABLE): experimental paths that are correct (parity-tested)
 // but not yet faster than the default ones:
 //   1 persistent pipelined fused forward k_resblock_fwd_pt, 2 persistent pipelined conv / dgrad k_conv_pt,
+//   8 transposed wgrad partial blocks (16 B stores in the epilogue, k_reduce_t): measured no gain
 //   4 wgrad partial block staged in shared memory + one TMA bulk store per CTA (measured: wgrad family 8.0 vs 7.75 ms per step
 //     with direct stores -- the serialised stage -> fence -> bulk store costs more than the 128 B-per-instruction stores it replaces)
 inline int& opt_enable_mask() { static int m = 0; return m; }

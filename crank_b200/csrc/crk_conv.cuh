@@ -287,6 +287,43 @@ __global__ void __launch_bounds__(256) k_reduce(const float* __restrict__ part, 
     }
 }
 
+// k_reduce for partial blocks whose weight part is TRANSPOSED, [k][TN][Rows] (+ [TN] bias partial; see WgradTcParams::tpart):
+// same fixed-order sums, read in the partials' own order (coalesced), written to out in the [k][Rows][TN] (+ [TN]) layout.
+// Rows % 4 == 0 and n % 4 == 0 (host-checked), so the 4 consecutive sources of a thread are 4 consecutive ci of one (j, co).
+__global__ void __launch_bounds__(256) k_reduce_t(const float* __restrict__ part, int nchunk, int n, float* __restrict__ out,
+                                                  int k, int Rows, int TN) {
+    __shared__ float4 red[8][32];
+    pdl_trigger();
+    pdl_wait();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int e = (blockIdx.x * 32 + tx) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < n)
+        for (int c = ty; c < nchunk; c += 8) {
+            const float4 v = *reinterpret_cast<const float4*>(part + (size_t)c * n + e);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && e < n) {
+        float4 t = red[0][tx];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { t.x += red[i][tx].x; t.y += red[i][tx].y; t.z += red[i][tx].z; t.w += red[i][tx].w; }
+        const float r4[4] = {t.x, t.y, t.z, t.w};
+        const int nW = k * Rows * TN;
+        if (e < nW) {
+            const int jc = e / Rows, ci = e - jc * Rows;          // (j * TN + co), first of 4 consecutive ci
+            const int j = jc / TN, co = jc - j * TN;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) out[((size_t)j * Rows + ci + i) * TN + co] = r4[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (e + i < n) out[e + i] = r4[i];
+        }
+    }
+}
+
 // per-chunk column sums (bias gradients): part[chunk * stride + n].  block = 8 row groups x 128 columns
 // (1024 threads), 4 independent accumulators per thread: 32 rows in flight per column; the 8 group
 // sums are combined through shared memory in fixed order (deterministic).
@@ -364,7 +401,7 @@ inline cudaError_t launch_wgrad_t(const WgradParams& p, dim3 grid, cudaStream_t 
 
 // tensor-core path (defined in crk_wgrad_tc.cuh): returns true when it handled the partials
 bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err,
-                  bool fused_bias, bool* bias_done);
+                  bool fused_bias, bool* bias_done, bool* tpart);
 
 // dW (and db when non-null) of one convolution.  cpt gives the packing of the G columns (TN=32*cpt).
 // dW and db must be adjacent (db == dW + k*Rows*TN, the packed weff layout) so that ONE deterministic
@@ -379,8 +416,8 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
     p.part_stride = stride;
     cudaError_t e = cudaSuccess;
     int nchunk = 0;
-    bool bias_done = false;
-    if (!wgrad_tc_try(p, TN, part, s, &nchunk, &e, fused_bias, &bias_done)) {
+    bool bias_done = false, tpart = false;
+    if (!wgrad_tc_try(p, TN, part, s, &nchunk, &e, fused_bias, &bias_done, &tpart)) {
         const WgradWork w = wgrad_work(p.B, p.T, p.k, p.Rows);
         nchunk = w.nchunk;
         p.tiles_per_chunk = w.tiles_per_chunk;
@@ -403,7 +440,8 @@ inline cudaError_t conv_wgrad(WgradParams p, int cpt, float* dW, float* db, floa
         if (e != cudaSuccess) return e;
     }
     const int n = (int)stride;
-    e = launch_pdl(k_reduce, dim3(cdiv(n, 128)), dim3(256), 0, s, (const float*)part, nchunk, n, dW, 0);
+    if (tpart) e = launch_pdl(k_reduce_t, dim3(cdiv(n, 128)), dim3(256), 0, s, (const float*)part, nchunk, n, dW, p.k, p.Rows, TN);
+    else e = launch_pdl(k_reduce, dim3(cdiv(n, 128)), dim3(256), 0, s, (const float*)part, nchunk, n, dW, 0);
     if (e != cudaSuccess) return e;
     e = launch_check();
     if (e != cudaSuccess) return e;

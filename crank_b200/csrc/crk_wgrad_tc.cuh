@@ -29,6 +29,12 @@ struct WgradTcParams {
     int nslot;         // X^T ring depth (2..4): hides the MMA completion latency of the per-tap handshake
     int bias;          // != 0: also write the per-chunk column sums of G (bias-gradient partial) behind the
                        // chunk's [k][Rows][TN] block, i.e. what k_colsum would have produced in a second pass over G
+    int tpart;         // != 0: the chunk's weight block is written TRANSPOSED, [k][TN][Rows]: a thread owns one co and 32
+                       // consecutive ci (the tensor-memory layout), so it stores 8 x 16 B instead of 32 x 4 B -- the epilogue
+                       // was suspected to be bound by the number of store instructions (128 B per warp instruction).
+                       // k_reduce_t sums the partials in this layout and writes dW in the [k][Rows][TN] layout.
+                       // Measured (opt-in, crk_debug_opt_enable 8): no gain -- k = 5 epilogue 15 K -> 20 K cycles, k = 1 6.1 K -> 5.5 K:
+                       // 16 B per lane at a 256 B stride writes half-filled sectors; the epilogue is bound by L2 sector writes.
 };
 
 // Transposed staging of src[frame t0+shift .. +64)[0..ncols):  elem(frame f, channel c) -> (f>>2)*cs + c*4 + (f&3).
@@ -261,6 +267,17 @@ __global__ void __launch_bounds__(TW, (SPLIT || NX > 4 || TW > 256) ? 1 : 2) k_w
         float v[32];
         if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
         if (co >= q.TN) continue;
+        if (q.tpart) {
+            float* dst = out + ((size_t)j * q.TN + co) * p.Rows + blk * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                if (blk * 32 + i < p.Rows) {
+                    float4 w4 = ntile_done > 0 ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (timeout_s) w4 = make_float4(poison, poison, poison, poison);
+                    *reinterpret_cast<float4*>(dst + i) = w4;
+                }
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const int ci = blk * 32 + i;
@@ -577,6 +594,17 @@ __global__ void __launch_bounds__(TW + 32, 1) k_wgrad_tc_raw(const WgradTcParams
             float v[32];
             if (ntile_done > 0) tc::tmem_ld32(tlane + j * q.Npad + blk * 32, v);
             if (co >= q.TN) continue;
+            if (q.tpart) {
+                float* dst = out + ((size_t)j * q.TN + co) * p.Rows + blk * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    if (blk * 32 + i < p.Rows) {
+                        float4 w4 = ntile_done > 0 ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (timeout_s) w4 = make_float4(poison, poison, poison, poison);
+                        *reinterpret_cast<float4*>(dst + i) = w4;
+                    }
+                continue;
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int ci = blk * 32 + i;
@@ -734,7 +762,7 @@ inline cudaError_t launch_wgrad_tc_raw_t(const WgradTcParams& q, int nchunk, cud
 // fused_bias: the caller wants the bias-gradient partial behind each chunk's weight partial; *bias_done
 // tells it whether this kernel produced it (else k_colsum must run)
 inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, int* nchunk, cudaError_t* err,
-                         bool fused_bias, bool* bias_done) {
+                         bool fused_bias, bool* bias_done, bool* tpart) {
     const int mode = precision_mode();
     if (mode == CRK_PREC_FP32 || (tc_disable_mask() & 4)) return false;
     const bool split = mode == CRK_PREC_TF32X3;
@@ -744,6 +772,8 @@ inline bool wgrad_tc_try(WgradParams& p, int TN, float* part, cudaStream_t s, in
     WgradTcParams q;
     q.p = p; q.p.part = part; q.p.tiles_per_chunk = w.tiles_per_chunk; q.TN = TN; q.Npad = Npad; q.dbg = dbg_take(CRK_K_WGRAD); q.nslot = wgrad_tc_nslot(Npad, split);
     q.gbuf = wgrad_tc_gbuf(Npad, split);
+    q.tpart = ((p.Rows & 3) == 0 && (p.part_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0 && (opt_enable_mask() & 8)) ? 1 : 0;
+    *tpart = q.tpart != 0;
     q.bias = (fused_bias && !(opt_disable_mask() & 2)) ? 1 : 0;
     *bias_done = q.bias != 0;
     *nchunk = w.nchunk;

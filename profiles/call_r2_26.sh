@@ -2,7 +2,7 @@
 # round 2, call 26: 16 worker warps in k_wgrad_tc_raw: parity + A/B (opt-disable 1024 = 8 warps) + phase stamps
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests/test_gpu_tc.py tests/test_gpu_kernels.py tests/test_gpu_fullsize.py tests/test_gpu_baseline_shapes.py tests/test_gpu_trainstep.py -m gpu -q -x 2>&1 | tail -4 > gpurun_out/r2_pytest_26.log; cat gpurun_out/r2_pytest_26.log
-for M in 0 1024; do
+for M in 0 2048; do
 CRANK_B200_OPT_DISABLE=$M timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager-gpu-baseline > gpurun_out/r2_bench_26_m$M.json 2> gpurun_out/r2_bench_26_m$M.err
 python - <<PY
 import json
