@@ -332,7 +332,7 @@ int crk_vq_argmin_fast(const float* x, int ldx, const float* opblob, long long* 
     const long long tiles = cdivl(F, 128);
     const int sms = device_sm_count();
     TimedLaunch tl(CRK_K_VQ_ARGMIN, (cudaStream_t)stream, 2.0 * F * 64.0 * K);
-    k_vq_argmin_tf32<<<(unsigned)(tiles < sms ? tiles : sms), 256, vq_fast_smem(K), (cudaStream_t)stream>>>(q);
+    k_vq_argmin_tf32<<<(unsigned)(tiles < sms ? tiles : sms), CRK_VQ_THREADS, vq_fast_smem(K), (cudaStream_t)stream>>>(q);
     API_TRY(launch_check());
     return CRK_OK;
 }

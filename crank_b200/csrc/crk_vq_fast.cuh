@@ -49,7 +49,11 @@ struct VqFastParams {
     const float* opblob;
 };
 
-__global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q) {
+// 512 threads: the bound scans are instruction-bound, and with 8 warps (2 per scheduler) latency-bound on top (round 2: the same
+// finding as in the wgrad kernels); 16 warps split each frame's K codes in four column parts instead of two.
+#define CRK_VQ_THREADS 512
+#define CRK_VQ_PARTS (CRK_VQ_THREADS / 128)
+__global__ void __launch_bounds__(CRK_VQ_THREADS, 1) k_vq_argmin_tf32(const VqFastParams q) {
     const VqArgminParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
@@ -57,9 +61,9 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
     __shared__ uint32_t tmem_base_s;
     __shared__ int timeout_s;
     __shared__ float xn_s[128];
-    __shared__ float mbu_s[2][128];
-    __shared__ float med_s[128];
-    __shared__ int mek_s[128];
+    __shared__ float mbu_s[CRK_VQ_PARTS][128];
+    __shared__ float med_s[CRK_VQ_PARTS][128];
+    __shared__ int mek_s[CRK_VQ_PARTS][128];
     __shared__ int best_s[128];
 
     const int K = p.K;
@@ -105,10 +109,11 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
         const int nlive = (int)min((long long)128, p.F - f0);
         // ---- stage the X tile once: chunk-major operand + row-major copy ----
         {
-            float4 v[8];
+            constexpr int NU = 2048 / CRK_VQ_THREADS;
+            float4 v[NU];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = threadIdx.x + u * 256, r = i >> 4, c4 = i & 15;
+            for (int u = 0; u < NU; ++u) {
+                const int i = threadIdx.x + u * CRK_VQ_THREADS, r = i >> 4, c4 = i & 15;
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r < nlive) {
                     const float* src = p.x + (size_t)(f0 + r) * p.ldx + c4 * 4;
@@ -117,8 +122,8 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = threadIdx.x + u * 256, r = i >> 4, c4 = i & 15;
+            for (int u = 0; u < NU; ++u) {
+                const int i = threadIdx.x + u * CRK_VQ_THREADS, r = i >> 4, c4 = i & 15;
                 *reinterpret_cast<float4*>(Xt + c4 * CSX + r * 4) = v[u];
                 float* d = xrows + r * 65 + c4 * 4;
                 d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
             }
             if (tc::elect_one()) tc::umma_commit(&bar_acc);
             __syncwarp();
-        } else if (threadIdx.x >= 128) {
+        } else if (threadIdx.x >= 128 && threadIdx.x < 256) {
             const int r = threadIdx.x - 128;
             const float* xr = xrows + r * 65;
             float s = 0.f;
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
         }
         if (it == 0) {
             ok &= tc::mbar_wait(&bar_w, 0);                               // wn_s / Wb visible to every thread
-            for (int k = threadIdx.x; k < K; k += 256) {
+            for (int k = threadIdx.x; k < K; k += CRK_VQ_THREADS) {
                 wa_s[k] = wn_s[k] * (1.f + CRK_VQ_TF32_RADIUS);
                 wb_s[k] = wn_s[k] * (1.f - CRK_VQ_TF32_RADIUS);
             }
@@ -160,8 +165,8 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
         // with the per-code tables wa = wn (1 + c), wb = wn (1 - c) in shared memory (c carries 28 % of slack over the
         // rigorous 2^-9: fp32 rounding of these expressions, ~1e-7 relative, cannot break the bounds)
         const int r = (warp & 3) * 32 + lane;
-        const int half = warp >> 2;
-        const int kbeg = half * (K >> 1), kend = kbeg + (K >> 1);
+        const int half = warp >> 2;                      // column part of this warp (0 .. CRK_VQ_PARTS-1)
+        const int kbeg = half * (K / CRK_VQ_PARTS), kend = kbeg + (K / CRK_VQ_PARTS);
         const float xn = xn_s[r];
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         float mub = INF;
@@ -177,7 +182,10 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
         }
         mbu_s[half][r] = mub;
         __syncthreads();
-        const float bu = fmaf(xn, 1.f + CRK_VQ_TF32_RADIUS, fminf(mbu_s[0][r], mbu_s[1][r]));     // best upper bound
+        float mall = mbu_s[0][r];
+#pragma unroll
+        for (int pp = 1; pp < CRK_VQ_PARTS; ++pp) mall = fminf(mall, mbu_s[pp][r]);
+        const float bu = fmaf(xn, 1.f + CRK_VQ_TF32_RADIUS, mall);     // best upper bound
         const float thr = bu - xn * (1.f - CRK_VQ_TF32_RADIUS);
         int cand[CRK_VQ_MAXCAND];
         int ncand = 0;
@@ -246,16 +254,18 @@ __global__ void __launch_bounds__(256, 1) k_vq_argmin_tf32(const VqFastParams q)
                 if (ex < ed) { ed = ex; ek = kk; }
             }
         }
-        if (half == 1) { med_s[r] = ed; mek_s[r] = ek; }
+        med_s[half][r] = ed; mek_s[half][r] = ek;
         __syncthreads();
         if (half == 0) {
-            if (med_s[r] < ed) { ed = med_s[r]; ek = mek_s[r]; }    // ties keep the lower index (half 0)
+#pragma unroll
+            for (int pp = 1; pp < CRK_VQ_PARTS; ++pp)           // ascending parts: ties keep the lower index
+                if (med_s[pp][r] < ed) { ed = med_s[pp][r]; ek = mek_s[pp][r]; }
             best_s[r] = ek == 0x7fffffff ? 0 : ek;
         }
         __syncthreads();
         if (threadIdx.x < nlive) p.idx[f0 + threadIdx.x] = (long long)best_s[threadIdx.x];
 #pragma unroll 2
-        for (int i = threadIdx.x; i < 128 * 16; i += 256) {
+        for (int i = threadIdx.x; i < 128 * 16; i += CRK_VQ_THREADS) {
             const int rr = i >> 4, c4 = i & 15;
             if (rr >= nlive) continue;
             const float4 ev = *(reinterpret_cast<const float4*>(Wb) + (size_t)c4 * CR + best_s[rr]);
