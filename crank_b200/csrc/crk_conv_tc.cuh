@@ -198,6 +198,9 @@ __device__ __forceinline__ void tc_stage_act_pro(float* hi, float* lo, int cs_fl
 // MODE 0: generic conv / dgrad (every prologue / epilogue option, scalar fallbacks);  MODE 1: gate backward;
 // MODE 2: conv / dgrad whose operands allow 128-bit accesses throughout and have no input multiplier (the
 // hot instances: every dgrad and 1x1 conv of the WaveNet stacks) -- one staging path, one epilogue path.
+#ifndef CRK_CONV_NSLOT2
+#define CRK_CONV_NSLOT2 2          // ring depth of the two-CTA/SM variant: 2 slots x 8 chunks.  Measured: 4 x 4 chunks in the same 33 KB is SLOWER (conv family 5.6 -> 6.6 ms per step: the per-step handshake outweighs the deeper prefetch)
+#endif
 #define CRK_CONV_GENERIC 0
 #define CRK_CONV_GATE 1
 #define CRK_CONV_FAST 2
@@ -215,8 +218,9 @@ __global__ void __launch_bounds__(256, (SPLIT && WIDE) ? 1 : 2) k_conv_tc(const 
     const ConvParams& p = q.p;
     extern __shared__ float4 crk_smem4[];
     float* smem = reinterpret_cast<float*>(crk_smem4);
-    constexpr int NSLOT = 2;
-    constexpr int SEG = (SPLIT && !WIDE) ? 8 : 16;     // channel chunks per ring slot
+    // ring: NSLOT slots of SEG channel chunks (see CRK_CONV_NSLOT2)
+    constexpr int NSLOT = (SPLIT && !WIDE) ? CRK_CONV_NSLOT2 : 2;
+    constexpr int SEG = (SPLIT && !WIDE) ? (32 / CRK_CONV_NSLOT2) / 2 : 16;     // channel chunks per ring slot
     constexpr int PHC = (SPLIT && !WIDE) ? 16 : 32;    // channel chunks staged per K phase
     __shared__ uint64_t bar_full[NSLOT];
     __shared__ uint64_t bar_free[NSLOT];
@@ -497,10 +501,11 @@ __global__ void __launch_bounds__(256, (SPLIT && WIDE) ? 1 : 2) k_conv_tc(const 
 inline size_t conv_tc_smem(const ConvTcParams& q, bool split, bool wide = false) {
     const int rowsX = CRK_TC_TM + (q.p.k - 1) * q.p.dil;
     const int kch = q.Kpad >> 2;
-    const int phc = (split && !wide) ? 16 : 32, segc = (split && !wide) ? 8 : 16;     // PHC / SEG of the kernel
+    const int phc = (split && !wide) ? 16 : 32, segc = (split && !wide) ? (32 / CRK_CONV_NSLOT2) / 2 : 16;     // PHC / SEG of the kernel
+    const int nslot = (split && !wide) ? CRK_CONV_NSLOT2 : 2;
     const size_t a = (size_t)(kch < phc ? kch : phc) * tc::chunk_rows(rowsX) * 4;
     const size_t seg = (size_t)(kch < segc ? kch : segc) * tc::chunk_rows(q.Npad) * 4;   // one half of a ring slot
-    const size_t pipe = (split ? 2 : 1) * a + (split ? 4 : 2) * seg;
+    const size_t pipe = (split ? 2 : 1) * a + (size_t)nslot * (split ? 2 : 1) * seg;
     const size_t stage = (size_t)CRK_TC_TM * (q.Npad | 1);      // epilogue transposition tile
     return (pipe > stage ? pipe : stage) * sizeof(float);
 }
