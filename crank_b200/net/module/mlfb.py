@@ -52,6 +52,11 @@ class MLFBLayer(nn.Module):
         basis = mel_basis(fs, fft_size, n_mels, fmin, fmax)
         self.register_buffer("mel_basis", torch.from_numpy(basis.T.copy()).float())  # (bins, n_mels)
 
+    def forward(self, x):
+        """(…, bins) magnitude spectrogram -> log10 mel (mlfb.py:36-43).  Stand-alone use only (plain torch ops on whatever
+        device x lives on); inside LogMelFilterBankLayer the projection is part of the fused kernel."""
+        return torch.clamp(torch.matmul(x, self.mel_basis), min=self.eps).log10()
+
 
 class STFTLayer(nn.Module):
     """Holds the STFT geometry and window of crank/net/module/mlfb.py:45-110; the transform itself runs inside the
@@ -95,6 +100,20 @@ class STFTLayer(nn.Module):
     @property
     def learnable(self):
         return self.window_type in ("param", "conv")
+
+    def forward(self, x):
+        """(B, n_samples) -> (B, frames, bins, 2) real / imaginary STFT like the reference layer (mlfb.py:92-110).  Stand-alone
+        use only (`torch.stft`, a library FFT): LogMelFilterBankLayer.forward never calls it, its transform is in-kernel."""
+        window = None
+        if self.window_type == "param":
+            window = self.window
+        elif self.window_type == "conv":
+            x = self.window_conv(x.unsqueeze(1)).mean(dim=1)
+        else:
+            window = torch.hann_window(self.win_length, dtype=x.dtype, device=x.device)
+        st = torch.stft(x, n_fft=self.fft_size, win_length=self.win_length, hop_length=self.hop_size, window=window,
+                        center=self.center, pad_mode=self.pad_mode, return_complex=True)
+        return torch.view_as_real(st).transpose(1, 2).float()
 
 
 class MLFBScalerLayer(nn.Module):

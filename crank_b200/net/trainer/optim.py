@@ -16,6 +16,14 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.capturable = bool(capturable)
 
+    def state_dict(self):
+        # capturable mode advances the step count on the device (graph replays never run this Python): mirror it into the host
+        # field the checkpoint carries, so that a resumed run continues with the right bias corrections
+        for st in self.state.values():
+            if "step_dev" in st:
+                st["step"] = int(st["step_dev"].item())
+        return super().state_dict()
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None

@@ -308,3 +308,47 @@ def test_offline_mlfb_extraction_wrapper_against_the_reference_fixture():
     # fp32 against the float64 fixture; quiet bins sit near the eps floor where log10 amplifies rounding
     assert np.abs(got - ref).max() < 2e-3 and np.abs(got - ref).mean() < 2e-5, (np.abs(got - ref).max(), np.abs(got - ref).mean())
     assert both.shape == (2, 1057, 80) and torch.allclose(both[0], torch.from_numpy(got))
+
+
+def test_mel_band_tables_reproduce_the_dense_basis():
+    """ops._mel_bands (the banded form of the mel basis the fused log-mel kernels read, and its transpose for the backward):
+    expanding the runs gives back the dense (bins, n_mels) matrix exactly."""
+    import numpy as np
+    import torch
+
+    from crank_b200 import ops
+    from crank_b200.net.module.mlfb import mel_basis
+
+    for fs, fmin, fmax in ((24000, 80, 7600), (22050, 80, 7600), (16000, 0, None)):
+        w = mel_basis(fs, 1024, 80, fmin, fmax).T.copy()            # (513, 80)
+        st, ln, of, bw, nnz, tst, tln, tof, tbw = ops._mel_bands(torch.from_numpy(w))
+        assert nnz <= ops.MEL_FUSED_MAXNNZ
+        dense = np.zeros_like(w)
+        for m in range(80):
+            dense[int(st[m]):int(st[m]) + int(ln[m]), m] = bw[int(of[m]):int(of[m]) + int(ln[m])].numpy()
+        assert np.array_equal(dense, w)
+        dense_t = np.zeros_like(w)
+        for k in range(513):
+            dense_t[k, int(tst[k]):int(tst[k]) + int(tln[k])] = tbw[int(tof[k]):int(tof[k]) + int(tln[k])].numpy()
+        assert np.array_equal(dense_t, w)
+
+
+def test_stft_and_mlfb_layers_stand_alone_match_the_fused_definition():
+    """STFTLayer.forward / MLFBLayer.forward (mlfb.py:36-110) compose to the same log-mel the oracle computes."""
+    import numpy as np
+    import torch
+
+    from crank_b200.net.module.mlfb import MLFBLayer, STFTLayer
+    from oracle import mel as omel
+
+    g = torch.Generator().manual_seed(0)
+    x = 0.1 * torch.randn(2, 4000, generator=g)
+    st = STFTLayer(fs=24000, hop_size=128, fft_size=1024, center=False)
+    ml = MLFBLayer(fs=24000, fft_size=1024, n_mels=80, fmin=80, fmax=7600)
+    spec = st(x)
+    got = ml(torch.sqrt(spec[..., 0] ** 2 + spec[..., 1] ** 2)).numpy()
+    basis = omel.mel_basis(24000, 1024, 80, 80, 7600).T.astype(np.float64)
+    ref = np.stack([np.log10(np.maximum(1e-10, omel.stft_mag(x[b].double().numpy(), 1024, 128, omel.hann(1024, True), center=False) @ basis))
+                    for b in range(2)])
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-4
