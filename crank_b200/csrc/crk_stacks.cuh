@@ -234,7 +234,10 @@ struct SideStream {
     bool ok = false;
 };
 inline SideStream* side_stream() {
-    static thread_local SideStream S;
+    static thread_local SideStream per_dev[16];           // one per device of this thread (streams belong to a device)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideStream& S = per_dev[dev];
     if (!S.ok) {
         if (cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         for (int i = 0; i < 64; ++i)
