@@ -7,6 +7,8 @@ LSGAN targets are constants, so `MSE(D(x)[mask], 1)` is a masked sum/count reduc
 scalar (no ones_like / masked_select tensors, trainer_lsgan.py:154-171).
 """
 
+import os
+
 import torch
 
 from ... import ops
@@ -24,6 +26,7 @@ class LSGANTrainer(VQVAETrainer):
         self.gan_flag = False
         self.cycle_flag = False
         self.stop_generator = False
+        self.batch_D_passes = os.environ.get("CRANK_B200_BATCH_D", "1") != "0"      # update_D: one pass over [real | fake]
         self._check_cycle_start()
         self._check_gan_start()
         self.stop_generator = False  # the reference resets it after the checks (trainer_lsgan.py:53)
@@ -87,9 +90,21 @@ class LSGANTrainer(VQVAETrainer):
             h = batch["org_h"]
         with torch.no_grad():       # only decoded.detach() is used below: no autograd graph, no saved activations
             outputs = self.model["G"].forward(batch["in_feats"], enc_h, dec_h, spkrvec)
-        real = self._discriminate(self.get_D_inputs(batch, batch["in_feats"], label="org"))
+        real_in = self.get_D_inputs(batch, batch["in_feats"], label="org")
+        fake_in = self.get_D_inputs(batch, outputs["decoded"].detach(), label="cv")
+        if self.batch_D_passes:
+            # ONE discriminator pass over [real | fake] along the batch axis instead of the reference's two
+            # (trainer_lsgan.py:168-178): the network has no cross-utterance coupling, so the outputs are the same
+            # numbers and the parameter gradient is the same sum; half the launches of the D update (~70 of ~900 per step)
+            # and one weight-gradient partial-sum epilogue instead of two.  (With dropout the two halves draw their masks
+            # from one RNG call instead of two.)
+            nb = real_in.shape[0]
+            both = self._discriminate(torch.cat([real_in, fake_in], dim=0))
+            real, fake = both[:nb], both[nb:]
+        else:
+            real = self._discriminate(real_in)
+            fake = self._discriminate(fake_in)
         loss = self.calculate_discriminator_loss(real, batch["org_h"], mask, loss, label="real")
-        fake = self._discriminate(self.get_D_inputs(batch, outputs["decoded"].detach(), label="cv"))
         loss = self.calculate_discriminator_loss(fake, h, mask, loss, label="fake")
         if phase == "train":
             self.step_model(loss, model="D")
