@@ -366,6 +366,14 @@ def run_b200(args, rank, local_rank, world):
     # ---- per-kernel timing (CUDA events on the launch stream), two extra steps each ----------------
     kern = {}
     ids = {"resblock_fwd": 1, "wgrad": 2, "conv": 3, "resblock_bwd_gate": 4, "vq_argmin": 5}
+    # the weight-gradient kernels normally run on a side stream, concurrently with the dgrad chain: event pairs around
+    # concurrent launches would charge each family for the other's time.  The attribution steps therefore run with the side
+    # stream off (option bit 512: every launch on one stream, the way ncu serialises them); `value` / `e2e` above were
+    # measured with it on.
+    opt_base = int(os.environ.get("CRANK_B200_OPT_DISABLE", "0"))
+    L.check(L.lib().crk_debug_opt_disable(opt_base | 512), "opt_disable")
+    for _ in range(2):
+        step_resident()
     for name, kid in ids.items():
         # every rank runs the extra steps (they contain collectives); rank 0's numbers are reported
         L.check(L.lib().crk_timing_enable(kid), "timing")
@@ -378,6 +386,7 @@ def run_b200(args, rank, local_rank, world):
                       "avg_us": 1e3 * tot.value / max(cnt.value, 1), "gflop_per_step": fl / 2 / 1e9,
                       "tflops": (fl / 1e12) / (tot.value * 1e-3) if tot.value > 0 else None}
     L.lib().crk_timing_enable(0)
+    L.check(L.lib().crk_debug_opt_disable(opt_base), "opt_disable")
     if world > 1:
         dist.barrier()
 
@@ -447,7 +456,8 @@ def run_b200(args, rank, local_rank, world):
                 "kernel": {"resblock_fwd": "k_resblock_fwd_tc2 (fused gated residual block forward)",
                            "conv": "k_conv_tc (dgrad / plain conv family)",
                            "wgrad": "k_wgrad_tc / k_wgrad_tc_raw (weight-gradient family)"}[dom] if args.precision != "fp32" else dom,
-                "selection": "the dense-contraction family with the largest share of the step; every family is listed under `families`",
+                "selection": "the dense-contraction family with the largest share of the step; every family is listed under `families`; "
+                             "family times are measured with the weight-gradient side stream off (serialised launches)",
                 "families": {k: {"ms_per_step": v["ms_per_step"], "tflops": v["tflops"],
                                  "frac": (v["tflops"] / peak_tf) if (v["tflops"] and peak_tf) else None}
                              for k, v in kern.items() if k != "vq_argmin"},
