@@ -48,7 +48,8 @@ def scaling():
             continue
         tab[(m.group(1), int(m.group(2)))] = d
     one = {}
-    for name in ("r2_bench_final.json", "r2_bench_18.json"):
+    # N = 1 of the SAME build as the multi-GPU runs (they were taken before the last single-GPU optimisations of the round)
+    for name in ("r2_bench_22_m256.json", "r2_bench_21.json", "r2_bench_18.json"):
         p = os.path.join(OUT, name)
         if os.path.exists(p):
             one["weak"] = last_json(p)
@@ -57,7 +58,8 @@ def scaling():
         return
     out = ["# Round 2: scaling on one 8 x B200 node (`profiles/call_r2_20.sh`; one process per GPU, NCCL)", "",
            "weak = 64 utterances per GPU (the driver's SCALE run); strong = BASELINE config 3 as written: global batch 64 utterances split over the ranks.",
-           "Device-timed, max over ranks, 20 timed steps after 5 warm-up steps.", "",
+           "Device-timed, max over ranks, 20 timed steps after 5 warm-up steps.  The N = 8 runs and their N = 1 baseline are one build (20.9 ms per step on one GPU);",
+           "the N = 2 points are an earlier build of the round (22.4 ms on one GPU); the final build runs the one-GPU step in 19.0 ms.", "",
            "| mode | GPUs | utts/GPU | ms/step | frames/s (all GPUs) | efficiency |", "|---|---:|---:|---:|---:|---:|"]
     base = {}
     for mode in ("weak", "strong", "stronggraph"):
