@@ -352,3 +352,46 @@ def test_stft_and_mlfb_layers_stand_alone_match_the_fused_definition():
                     for b in range(2)])
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-4
+
+
+def test_dev_wav_generation_host_logic(tmp_path):
+    """BaseTrainer._generate_cvwav (basetrainer.py:322-420 of the reference): inverse scaler, grouping of equal-length
+    utterances into one Griffin-Lim batch, sample selection, file naming and 16-bit WAV writing -- on CPU with emulated
+    ops (the Griffin-Lim itself is plain torch; checked against the oracle in tests/test_cpu_griffinlim.py)."""
+    import wave
+
+    from crank_b200.conf import vcc2020_conf
+    from crank_b200.net.trainer import TrainerWrapper, get_criterion, get_model, get_optimizer, get_scheduler
+    from crank_b200.synthetic import make_batch, spkr_dict
+
+    class _Scaler:      # sklearn StandardScaler surface
+        mean_ = np.linspace(-1.0, 1.0, 80)
+        scale_ = np.linspace(0.5, 1.5, 80)
+
+    conf = vcc2020_conf(trainer_type="vqvae")
+    with emulated_ops():
+        pm = get_model(conf, S, device="cpu")
+        opt = get_optimizer(conf, pm)
+        P = TrainerWrapper("vqvae", model=pm, optimizer=opt, criterion=get_criterion(conf),
+                           dataloader={"spkrs": spkr_dict(S)}, writer={"train": _W(), "dev": _W()},
+                           expdir=str(tmp_path), conf=conf, feat_conf=conf["feature"],
+                           scheduler=get_scheduler(conf, opt), scaler={"mlfb": _Scaler()}, resume=0, device="cpu", n_jobs=1)
+        P.tqdm.close()
+        batch = make_batch(4, 64, S, seed=3, ragged=False)
+        batch["flen"] = torch.tensor([64, 40, 64, 40])
+        with torch.no_grad():
+            out = P._convert(batch, None)
+            # keep the log-mel in a sane range so that 10**x does not overflow in the pinv projection
+            out["decoded"] = out["decoded"].clamp(-2.0, 2.0)
+            none = P._generate_cvwav(batch, out, None, tdir="eval_wav", save_decoded=False)
+            wavs = P._generate_cvwav(batch, out, "spk1", tdir="dev_wav", save_hdf5=False, n_samples=-1)
+    assert none == {}
+    assert len(wavs) == 4
+    hop = conf["feature"]["hop_size"]
+    for n, (path, y) in enumerate(sorted(wavs.items(), key=lambda kv: str(kv[0]))):
+        assert str(path).endswith("_cv-spk1.wav") and "dev_wav" in str(path)
+        assert torch.isfinite(y).all()
+        with wave.open(str(path), "rb") as f:
+            assert f.getframerate() == conf["feature"]["fs"] and f.getsampwidth() == 2 and f.getnframes() == y.numel()
+    lengths = sorted(int(y.numel()) for y in wavs.values())
+    assert lengths == sorted([hop * 39, hop * 39, hop * 63, hop * 63])
