@@ -181,8 +181,9 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step_count):
     p.addcdiv_(m, denom, value=-(lr / bc1))
 
 
-def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None):
-    """crk_logmel_fwd: frames start at m*hop (no centring here), |rFFT(window * frame)| . mel_basis -> log10."""
+def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None, fused=None):
+    """crk_logmel_fwd / crk_logmel_fused_fwd: frames start at m*hop (no centring here), |rFFT(window * frame)| . mel_basis -> log10.
+    Differentiable in wav and window: also the stand-in of ops.logmel_learnable (crk_logmel_fused_bwd)."""
     wav = wav.float()
     frames = wav.unfold(-1, n_fft, hop) * window                        # (B, M, n_fft)
     mag = torch.fft.rfft(frames, dim=-1).abs()
@@ -209,12 +210,13 @@ def emulated_ops():
              (ops, "MaskedLossFn", ops.MaskedLossFn), (ops, "CrossEntropyFn", ops.CrossEntropyFn),
              (ops, "StftLossFn", ops.StftLossFn), (ops, "adam_step", ops.adam_step),
              (ops, "adam_step_dev", ops.adam_step_dev), (ops, "logmel", ops.logmel),
-             (lib, "require_cuda", lib.require_cuda)]
+             (ops, "logmel_learnable", ops.logmel_learnable), (lib, "require_cuda", lib.require_cuda)]
     models.WavenetFn, models.ConvstackFn = WavenetEmu, ConvstackEmu
     ops.VQFn, ops.vq_ema_update = VQEmu, vq_ema_update
     ops.MaskedLossFn, ops.CrossEntropyFn = MaskedLossEmu, CrossEntropyEmu
     ops.StftLossFn, ops.adam_step, ops.adam_step_dev = StftLossEmu, adam_step, adam_step_dev
     ops.logmel = logmel
+    ops.logmel_learnable = logmel
     lib.require_cuda = lambda *a, **k: None
     try:
         yield

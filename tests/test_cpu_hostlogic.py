@@ -395,3 +395,38 @@ def test_dev_wav_generation_host_logic(tmp_path):
             assert f.getframerate() == conf["feature"]["fs"] and f.getsampwidth() == 2 and f.getnframes() == y.numel()
     lengths = sorted(int(y.numel()) for y in wavs.values())
     assert lengths == sorted([hop * 39, hop * 39, hop * 63, hop * 63])
+
+
+@pytest.mark.parametrize("window", ["hann", "param", "conv"])
+def test_raw_front_end_window_types_host_logic(window):
+    """LogMelFilterBankLayer (mlfb.py:72-171) for the three window types with emulated ops: `hann` runs without autograd,
+    `param` exposes a learnable window parameter (state-dict key stft_layer.window) that receives a gradient, `conv` a learnable
+    pre-filter (stft_layer.window_conv.0.*) that does; centre padding and the scaler epilogue as in the reference layer."""
+    from crank_b200.net.module.mlfb import LogMelFilterBankLayer
+
+    class _Scaler:
+        mean_ = np.zeros(80)
+        var_ = np.ones(80) * 4.0
+
+    torch.manual_seed(2)
+    with emulated_ops():
+        layer = LogMelFilterBankLayer(fs=24000, hop_size=128, fft_size=1024, win_length=1024, window=window, center=True,
+                                      n_mels=80, fmin=80, fmax=7600, scaler=_Scaler())
+        x = 0.1 * torch.randn(2, 4096)
+        out = layer(x)
+        assert out.shape == (2, 1 + 4096 // 128, 80)
+        keys = set(layer.state_dict())
+        if window == "hann":
+            assert not out.requires_grad and not any(k.startswith("stft_layer.window") for k in keys)
+        else:
+            out.square().mean().backward()
+            if window == "param":
+                assert "stft_layer.window" in keys
+                g = layer.stft_layer.window.grad
+            else:
+                assert {"stft_layer.window_conv.0.weight", "stft_layer.window_conv.0.bias"} <= keys
+                g = layer.stft_layer.window_conv[0].weight.grad
+            assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
+        # the scaler epilogue: (x - 0) / 2
+        layer.scaler_layer = None
+        assert torch.allclose(layer(x).detach() / 2.0, out.detach(), atol=1e-5)
