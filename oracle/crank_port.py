@@ -302,7 +302,20 @@ def build_models(conf, spkr_size):
 
 
 def build_optimizers(conf, model):
-    return {k: torch.optim.Adam(model[k].parameters(), lr=conf["optim"][k]["lr"])
+    """crank/net/trainer/utils.py:40-58: adam -> torch.optim.Adam; radam / lamb -> the restated third-party optimizers of
+    oracle/optim_port.py (torch_optimizer / pytorch_lamb are absent here)."""
+    from . import optim_port
+
+    def one(kind, params, lr):
+        if kind == "adam":
+            return torch.optim.Adam(params, lr=lr)
+        if kind == "radam":
+            return optim_port.RAdam(params, lr=lr)
+        if kind == "lamb":
+            return optim_port.Lamb(params, lr=lr)
+        raise ValueError("Invalid optimizer type")
+
+    return {k: one(conf["optim"][k].get("type", "adam"), model[k].parameters(), conf["optim"][k]["lr"])
             for k in ["G", "D", "C", "SPKRADV"] if k in model}
 
 

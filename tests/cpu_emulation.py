@@ -193,6 +193,34 @@ def logmel(wav, window, mel_basis, n_fft, hop, eps=1e-10, mean=None, std=None, f
     return out
 
 
+def radam_step(p, g, m, v, lr, beta1, beta2, eps, step_count):
+    """crk_radam_step: torch_optimizer.RAdam on one flat tensor."""
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    beta2_t = beta2 ** step_count
+    n_max = 2 / (1 - beta2) - 1
+    n_sma = n_max - 2 * step_count * beta2_t / (1 - beta2_t)
+    if n_sma >= 5:
+        step_size = lr * math.sqrt((1 - beta2_t) * (n_sma - 4) / (n_max - 4) * (n_sma - 2) / n_sma * n_max / (n_max - 2)) / (1 - beta1 ** step_count)
+        p.addcdiv_(m, v.sqrt().add_(eps), value=-step_size)
+    else:
+        p.add_(m, alpha=-lr / (1 - beta1 ** step_count))
+
+
+def lamb_step(p, g, m, v, upd, seg_off, seg_len, trust, lr, beta1, beta2, eps):
+    """crk_lamb_step: pytorch_lamb.Lamb with one trust ratio per segment of the flat pack."""
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    upd.copy_((m / v.sqrt().add(eps)).reshape(-1))
+    pf = p.view(-1)
+    for i, (o, n) in enumerate(zip(seg_off.tolist(), seg_len.tolist())):
+        wn = pf[o:o + n].pow(2).sum().sqrt().clamp(0, 10)
+        an = upd[o:o + n].pow(2).sum().sqrt()
+        t = 1.0 if (wn == 0 or an == 0) else float(wn / an)
+        trust[i] = t
+        pf[o:o + n].add_(upd[o:o + n], alpha=-lr * t)
+
+
 def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, step_dev):
     """crk_adam_step_dev: the counter lives in a tensor and is incremented by the call."""
     step_dev += 1
@@ -210,13 +238,15 @@ def emulated_ops():
              (ops, "MaskedLossFn", ops.MaskedLossFn), (ops, "CrossEntropyFn", ops.CrossEntropyFn),
              (ops, "StftLossFn", ops.StftLossFn), (ops, "adam_step", ops.adam_step),
              (ops, "adam_step_dev", ops.adam_step_dev), (ops, "logmel", ops.logmel),
-             (ops, "logmel_learnable", ops.logmel_learnable), (lib, "require_cuda", lib.require_cuda)]
+             (ops, "logmel_learnable", ops.logmel_learnable), (ops, "radam_step", ops.radam_step),
+             (ops, "lamb_step", ops.lamb_step), (lib, "require_cuda", lib.require_cuda)]
     models.WavenetFn, models.ConvstackFn = WavenetEmu, ConvstackEmu
     ops.VQFn, ops.vq_ema_update = VQEmu, vq_ema_update
     ops.MaskedLossFn, ops.CrossEntropyFn = MaskedLossEmu, CrossEntropyEmu
     ops.StftLossFn, ops.adam_step, ops.adam_step_dev = StftLossEmu, adam_step, adam_step_dev
     ops.logmel = logmel
     ops.logmel_learnable = logmel
+    ops.radam_step, ops.lamb_step = radam_step, lamb_step
     lib.require_cuda = lambda *a, **k: None
     try:
         yield

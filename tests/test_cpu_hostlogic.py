@@ -87,6 +87,8 @@ def test_product_train_steps_match_oracle_with_emulated_ops(kind):
     ("lsgan", dict(encoder_detach=True)),
     ("lsgan", dict(train_first="G")),
     ("vqvae", dict(use_cyclic_training=True, n_steps_cycle_start=-1)),
+    ("lsgan", dict(optim={m: {"type": "radam"} for m in ("G", "D", "C", "SPKRADV")})),
+    ("vqvae", dict(optim={m: {"type": "lamb"} for m in ("G", "D", "C", "SPKRADV")})),
 ])
 def test_product_host_logic_on_config_variants(kind, overrides):
     _run(kind, overrides, T=176 if overrides.get("causal") else 96, steps=1 if overrides.get("causal") else 2)
