@@ -73,17 +73,25 @@ def main():
         P1 = build(kind, S, dev)
         init = state(P1)
         ref_losses = []
+        ref_state0 = None
         for i in range(STEPS):
             random.seed(100 + i)
             ref_losses.append(P1.train(to_device(whole[i], dev), "train"))
+            if i == 0:
+                ref_state0 = state(P1)
         ref_state = state(P1)
     dist.barrier()
     _dp.enable()
     P = build(kind, S, dev)
     dp_losses = []
+    dp_state0 = None
     for i in range(STEPS):
         random.seed(100 + i)
         dp_losses.append(P.train(to_device(part(whole[i], rank), dev), "train"))
+        if i == 0:
+            _dp.flush()
+            torch.cuda.synchronize()
+            dp_state0 = state(P)
     _dp.flush()
     torch.cuda.synchronize()
     dp_state = state(P)
@@ -104,16 +112,26 @@ def main():
                 worst_buf = max(worst_buf, (((dp_state[k] - v).abs().max() / v.abs().max().clamp_min(1e-30)).item(), k))
             else:
                 worst_rms = max(worst_rms, (rms, k))
+        # after the FIRST step no VQ index can have flipped (both runs quantise with identical codebooks): the movement of every
+        # tensor must agree to summation-order noise there; later steps may amplify near-tie flips of a barely trained codebook
+        worst_rms0 = (0.0, "")
+        for k, v in ref_state0.items():
+            mo, mp = v - init[k], dp_state0[k] - init[k]
+            if mo.abs().max().item() < 1e-12 or "ema_" in k or "embedding.weight" in k:
+                continue
+            worst_rms0 = max(worst_rms0, (((mp - mo).pow(2).mean().sqrt() / mo.pow(2).mean().sqrt()).item(), k))
         ok = worst_loss[0] <= 1e-4 and worst_rms[0] <= 3e-2 and worst_buf[0] <= 1e-3
         out = {"what": f"{world} ranks x {b} utterances == 1 device x {world * b} utterances, {kind}, T={T}, ragged masks, "
                        f"{STEPS} steps, 3xTF32 kernels, side-stream overlap {'on' if _dp._state['overlap'] else 'off'}",
                "worst_loss_rel_err": worst_loss, "worst_parameter_movement_rms_err": worst_rms,
                "worst_codebook_or_ema_buffer_rel_err": worst_buf, "pass": bool(ok),
+               "worst_parameter_movement_rms_err_after_step0": worst_rms0, "pass_step0": bool(worst_rms0[0] <= 1e-3),
                "losses_step1_ref": ref_losses[-1], "losses_step1_dp": dp_losses[-1]}
         os.makedirs("gpurun_out", exist_ok=True)
         json.dump(out, open(f"gpurun_out/dp_equiv_{kind}_{world}gpu.json", "w"), indent=1)
         print(json.dumps({k: out[k] for k in ("what", "worst_loss_rel_err", "worst_parameter_movement_rms_err",
-                                              "worst_codebook_or_ema_buffer_rel_err", "pass")}))
+                                              "worst_codebook_or_ema_buffer_rel_err", "pass",
+                                              "worst_parameter_movement_rms_err_after_step0", "pass_step0")}))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
